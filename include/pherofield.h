@@ -1,0 +1,285 @@
+/*
+ * pherofield.h — C ABI of the B200-native pheromone-field hot path.
+ *
+ * This is the drop-in boundary for the per-tick pheromone update (deposit, evaporation,
+ * diffusion) and the agent loop (sense pheromone -> pick a heading -> move) of
+ * ChitteshKumar/swarm_robotics_pheromones. The reference has no FFI of its own: its boundary is
+ * five Python methods and two tick drivers. Each entry point below names the
+ * reference interface (file:line, relative to the reference checkout) that it replaces.
+ * `sup`  = Phase-3/pheromone_algo_supervisor.py, `algo` = Phase-3/pheromone_algo.py,
+ * `graph` = Phase-3/graph.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types, no exceptions across the boundary.
+ *   - every function returns 0 (PF_OK) or a negative PF_E* code; pf_last_error(h) has the text.
+ *   - array arguments are DEVICE pointers owned by the caller (torch tensors as the buffer
+ *     carrier) unless the name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *   - a handle is not thread-safe; distinct handles are independent.
+ *   - there is no CPU fallback: without a CUDA device pf_create fails with PF_ECUDA.
+ *
+ * Grid convention (algo:351 `pheromone_grid[int(x)][int(y)] += intensity`): the FIRST world
+ * coordinate (x) selects the row, the second (y) the column; indices are truncated toward zero.
+ * Multi-GPU row strips therefore partition the x axis.
+ */
+#ifndef PHEROFIELD_H
+#define PHEROFIELD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+#define PF_MAX_CHANNELS 4
+#define PF_MAX_FOOD 16
+
+/* error codes */
+#define PF_OK 0
+#define PF_EINVAL (-1)   /* bad argument / config */
+#define PF_ECUDA (-2)    /* CUDA runtime error (text in pf_last_error) */
+#define PF_ENOMEM (-3)   /* device allocation failed */
+#define PF_ESTATE (-4)   /* call not valid in this state (e.g. sharded handle, missing ghosts) */
+
+/* robot states, sup:180-183 (RobotState). 0 marks an empty agent slot (multi-GPU holes). */
+#define PF_STATE_EMPTY 0
+#define PF_STATE_SEARCHING 1
+#define PF_STATE_HOMING 2
+#define PF_STATE_IDLE 3
+
+/* the five sensed directions in the reference's dict order, sup:390 */
+#define PF_DIR_CURRENT 0
+#define PF_DIR_FRONT 1
+#define PF_DIR_BACK 2
+#define PF_DIR_LEFT 3
+#define PF_DIR_RIGHT 4
+
+/* discrete decision of adjust_robot_behavior, sup:429-516 */
+#define PF_DEC_STRAIGHT 0 /* "no change needed": both wheels = v            sup:463-466,501-504 */
+#define PF_DEC_LEFT 1     /* SEARCHING sup:455-458; HOMING sup:491-494                          */
+#define PF_DEC_RIGHT 2    /* SEARCHING sup:459-462; HOMING sup:496-500                          */
+#define PF_DEC_KEEP 3     /* HOMING inside home radius, no branch taken: speeds persist sup:489-500 */
+#define PF_DEC_STOP 4     /* reached home sup:510-513                                          */
+#define PF_DEC_NONE 5     /* no decision this tick (pre-start random walk sup:736-744, IDLE, empty) */
+
+/* sense geometry */
+#define PF_SENSE_WORLD 0   /* fixed world-frame cell offsets (mirrors sup:399-414, "ref-DRUL") */
+#define PF_SENSE_HEADING 1 /* offsets rotated with the agent heading, sense_dist metres away   */
+
+/* agent meta word: one u32 per agent */
+#define PF_META_STATE_MASK 0x3u        /* bits 0-1: PF_STATE_*                                  */
+#define PF_META_MOVED 0x4u             /* bit 2: has_moved() result for the NEXT deposit sup:260 */
+#define PF_META_DEC_SHIFT 3            /* bits 3-5: last PF_DEC_*                               */
+#define PF_META_DEC_MASK 0x38u
+#define PF_META_CARRY 0x40u            /* bit 6: carrying food (fsm mode)                       */
+#define PF_META_COUNT_SHIFT 8          /* bits 8-31: deposits made so far (len(global grid))    */
+
+/* step flags */
+#define PF_STEP_DEPOSIT 0x1u /* run deposit_pheromone                                   sup:577 */
+#define PF_STEP_SENSE 0x2u   /* run sense + adjust (off before t = 5 s)                 sup:581 */
+#define PF_STEP_FIELD 0x4u   /* run evaporate(+diffuse)                       algo:354, sup:594 */
+#define PF_STEP_MOVE 0x8u    /* integrate the diff-drive stand-in (Webots physics)              */
+#define PF_STEP_ALL 0xFu
+
+typedef struct pf_config {
+  int32_t abi_version;  /* must be PF_ABI_VERSION */
+  int32_t device;       /* CUDA device ordinal */
+
+  /* ---- field storage (algo:244 grid, generalised) ---- */
+  int32_t H, W, C;      /* global rows (x), cols (y), channels */
+  int32_t row0, row1;   /* rows [row0,row1) owned by this handle; 0,H when not sharded */
+  float cell_size;      /* metres per cell */
+  float origin_x;       /* world x of the low edge of row 0 */
+  float origin_y;       /* world y of the low edge of col 0 */
+
+  /* ---- evaporate + diffuse: f' = keep * (f + D * L(f)) ---- */
+  int32_t stencil;                  /* 0 = evaporate only (algo:354-356), 5 or 9 point Laplacian */
+  float evap_keep[PF_MAX_CHANNELS]; /* (1 - evaporation_rate); reference 1-0.1      algo:248,356 */
+  float diffusion[PF_MAX_CHANNELS]; /* D; 0 = off. 9-point uses D/6 folded on the host           */
+  float delete_threshold;           /* values <= this become 0 (sup:603); <= 0 disables          */
+
+  /* ---- deposit rule (sup:230-234, 291-358) ---- */
+  float intensity_explore; /* 1.0  sup:232 */
+  float intensity_high;    /* 20.0 sup:233, every `high_every`-th SEARCHING deposit sup:316-318 */
+  float intensity_homing;  /* 5.0  sup:234 */
+  int32_t high_every;      /* 3 */
+  float move_threshold;    /* 0.0015 m, sup:260 */
+  int32_t deposit_channel[4]; /* channel written by an agent in state s (index PF_STATE_*) */
+  int32_t sense_channel[4];   /* channel read by an agent in state s */
+
+  /* ---- sense geometry (sup:379-417) ---- */
+  int32_t sense_mode;       /* PF_SENSE_* */
+  int32_t sense_drow[5];    /* PF_SENSE_WORLD: row offset (x axis) per PF_DIR_* */
+  int32_t sense_dcol[5];    /* PF_SENSE_WORLD: col offset (y axis) per PF_DIR_* */
+  float sense_dist;         /* PF_SENSE_HEADING: metres from the agent centre */
+
+  /* ---- decide (sup:185-226 PID, sup:429-516) ---- */
+  float pid_kp, pid_kd;     /* 1.0, 0.01 (ki is never applied, sup:217-218) */
+  float cruise_speed;       /* desiredV = 1.0 rad/s, sup:197 */
+  float max_speed;          /* MAX_SPEED = 3.14 rad/s, sup:74 */
+  float braitenberg_l;      /* sum_j coeff[j][0]*(1 - ps_j/512) precomputed, sup:468-470 */
+  float braitenberg_r;      /* sum_j coeff[j][1]*(1 - ps_j/512) */
+  float home_radius;        /* 0.7 m, sup:489 */
+  float home_lo_cm, home_hi_cm; /* reachedHome window 5..6 (0.05 <= round(d,2) <= 0.06) sup:667 */
+  float nest_x, nest_y;     /* start_position, sup:248 */
+  int32_t n_food;           /* >= 1 */
+  float food_x[PF_MAX_FOOD], food_y[PF_MAX_FOOD]; /* get_food_position, sup:419-422 */
+  float food_radius;        /* fsm: SEARCHING -> HOMING inside this distance (camera stand-in) */
+  int32_t fsm;              /* 0: states never change (supervisor without camera);
+                               1: SEARCHING->HOMING at food, HOMING->SEARCHING at nest
+                                  (experiment2.py:615-616, 746-764) */
+
+  /* ---- move: diff-drive stand-in for Webots physics ---- */
+  float dt;                 /* 0.064 s: two 32 ms Webots steps per controller tick */
+  float wheel_radius;       /* 0.02 m,  E-puck.proto:100 */
+  float axle_length;        /* 0.052 m, E-puck.proto:86  */
+} pf_config;
+
+/* Agents, structure-of-arrays, caller-owned device memory. `n` slots are processed; slots whose
+ * state is PF_STATE_EMPTY are skipped. gid is only read by migration and may be NULL otherwise. */
+typedef struct pf_agents {
+  int64_t n;
+  float* x;       /* world x (row axis) */
+  float* y;       /* world y (col axis) */
+  float* theta;   /* heading, radians in [-pi, pi] */
+  float* wl;      /* adjusted_left_speed, persists between ticks  sup:249 */
+  float* wr;      /* adjusted_right_speed                          sup:250 */
+  uint32_t* meta; /* PF_META_* */
+  uint32_t* gid;  /* global agent id (stable across migration) */
+} pf_agents;
+
+typedef struct pf_counters {
+  uint64_t ticks;
+  uint64_t deposits;        /* agents that deposited */
+  uint64_t decisions[6];    /* histogram over PF_DEC_* */
+  uint64_t food_grabbed;    /* fsm: SEARCHING->HOMING transitions  (experiment2.py:752-755) */
+  uint64_t food_delivered;  /* fsm: HOMING->SEARCHING at nest      (experiment2.py:615-616) */
+  uint64_t migrated_out;    /* agents packed for a neighbour strip */
+  uint64_t migrated_in;
+  uint64_t migrate_dropped; /* records that did not fit a send buffer or found no empty slot */
+} pf_counters;
+
+typedef struct pf_handle pf_handle;
+
+/* -------------------------------------------------------------------------------------------
+ * lifecycle
+ * ------------------------------------------------------------------------------------------- */
+int pf_abi_version(void);
+
+/* Fill `cfg` with the reference constants (sup:230-250, sup:74-77, algo:244-249) for an H x W x C
+ * field. Replaces the hard-coded constants of PheromoneAlgorithm.__init__. */
+int pf_config_default(pf_config* cfg, int32_t H, int32_t W, int32_t C);
+
+/* Allocate the double-buffered fp32 SoA field [2][C][rows+2 ghost][pitch] in HBM, zeroed, plus the
+ * sort scratch. Replaces `pheromone_grid = [[0.0]*10 ...]` (algo:244) and
+ * `self.pheromone_grids = {}` (sup:237). */
+int pf_create(const pf_config* cfg, pf_handle** out);
+int pf_destroy(pf_handle* h);
+const char* pf_last_error(const pf_handle* h); /* h may be NULL: last create error */
+int pf_get_config(const pf_handle* h, pf_config* out);
+
+/* Reserve scratch for up to `max_agents` per deposit call (sort keys, values, cub temp).
+ * Called implicitly (and synchronously) on first use when not called up front. */
+int pf_reserve_agents(pf_handle* h, int64_t max_agents);
+
+/* -------------------------------------------------------------------------------------------
+ * field access
+ * ------------------------------------------------------------------------------------------- */
+/* Device pointer to local row 0 (global row cfg.row0) of `channel` in the current (which=0) or
+ * next (which=1) buffer; the ghost rows are at ptr - pitch and ptr + rows*pitch. pitch in floats. */
+int pf_field_ptr(pf_handle* h, int which, int channel, float** ptr, int64_t* pitch);
+int pf_field_fill(pf_handle* h, int channel, float value, void* stream);
+/* copy rows [row0,row1) x W of one channel from/to a dense host array [rows][W] */
+int pf_field_upload_host(pf_handle* h, int channel, const float* src_host, void* stream);
+int pf_snapshot_host(pf_handle* h, int channel, float* dst_host, void* stream);
+/* Write the reflect (zero-flux) ghost rows of the CURRENT buffer at the arena's outer edges
+ * (row0 == 0 and/or row1 == H). Interior strip edges are filled by the halo exchange. */
+int pf_fill_ghosts(pf_handle* h, void* stream);
+/* fp64 sum of one channel over the owned rows, written to *sum_host after a stream sync. */
+int pf_field_sum_host(pf_handle* h, int channel, double* sum_host, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * the hot path
+ * ------------------------------------------------------------------------------------------- */
+/* Deterministic deposit: cell = (int((x-ox)/cs), int((y-oy)/cs)); agents are radix-sorted by
+ * (channel, cell) (stable => agent order inside a cell), each cell's amounts are summed in that
+ * fixed order by a warp-aggregated segmented sum, and the total is added to the field with one
+ * store per touched cell. No atomics. `channel` may be NULL (all channel 0). Positions outside
+ * rows [row0,row1) or outside the arena are skipped.
+ * Replaces `pheromone_grid[int(x)][int(y)] += intensity` (algo:351), the dict insert of
+ * deposit_pheromone (sup:312-318, 346-348) and `heatmap[..] += 20` (graph:23). */
+int pf_deposit(pf_handle* h, int64_t n, const float* x, const float* y, const float* amount,
+               const uint8_t* channel, void* stream);
+
+/* Deposit driven by agent state: gate on has_moved (sup:308-310), amount by state and the
+ * every-3rd rule on the agent's own deposit counter (sup:312-318, 346-348), channel by state.
+ * Updates meta (counter). Replaces PheromoneAlgorithm.deposit_pheromone (sup:291-358). */
+int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream);
+
+/* Fused evaporate + diffuse, `nsteps` times, swapping the double buffer each step. Reflect
+ * boundary at the arena edge. On a sharded handle (row0 > 0 or row1 < H) only nsteps == 1 is
+ * accepted and the ghost rows of the current buffer must have been exchanged by the caller.
+ * Replaces `grid[i][j] *= (1-evaporation_rate)` (algo:354-356); the diffusion term has no
+ * reference arithmetic and follows oracle/pf_oracle.c. */
+int pf_step_field(pf_handle* h, int nsteps, void* stream);
+/* Sharded driver pieces: compute local rows [row_begin,row_end) of the next buffer without
+ * swapping (interior rows first while the halo is in flight, edge rows after), then pf_swap. */
+int pf_step_field_rows(pf_handle* h, int row_begin, int row_end, void* stream);
+int pf_swap(pf_handle* h);
+
+/* Gather the five DRUL values per agent: out5[i*5 + PF_DIR_*]; NaN marks a direction whose cell
+ * lies outside the arena (the reference's empty list). `state` may be NULL (channel of
+ * SEARCHING). Replaces PheromoneAlgorithm.sense_pheromone (sup:379-417). */
+int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y, const float* theta,
+             const uint32_t* meta, float* out5, void* stream);
+
+/* sense -> ordered arg-max -> PID -> wheel speeds -> diff-drive move, one thread per agent.
+ * flags: PF_STEP_SENSE and/or PF_STEP_MOVE. `decisions_out` (u8 per agent) may be NULL.
+ * Replaces sense_pheromone + adjust_robot_behavior + PIDController.update
+ * (sup:379-417, 429-516, 185-226) and stands in for Webots physics. */
+int pf_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* decisions_out,
+                   void* stream);
+
+/* Whole ticks in the reference order deposit -> sense/decide -> evaporate/diffuse -> move
+ * (sup:575-607, 753-754). Sensing is enabled once time >= start_delay (5 s, sup:581,732);
+ * before that no deposit happens either (startPheromone is not called, sup:731-744).
+ * Not valid on a sharded handle (the host drives the exchange between the phases).
+ * Replaces Controller.startPheromone / Controller.homing (sup:565-607, 627-663). */
+int pf_step(pf_handle* h, const pf_agents* a, int nsteps, void* stream);
+int pf_set_time(pf_handle* h, double time_s, double start_delay_s);
+int pf_get_time(const pf_handle* h, double* time_s, uint64_t* ticks);
+
+/* I * exp(-rate * elapsed) elementwise in fp64. Replaces evaporate_pheromone (sup:519-525). */
+int pf_evaporate_trail(pf_handle* h, int64_t n, const double* elapsed, const double* intensity,
+                       double rate, double* out, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * multi-GPU row strips (no reference counterpart)
+ * ------------------------------------------------------------------------------------------- */
+/* Agents whose row left [row0,row1) are appended (ordered by slot) to the up (row < row0) or
+ * down (row >= row1) send buffer as 8-word (32 B) records {x,y,theta,wl,wr,meta,gid,0}; their slot
+ * becomes PF_STATE_EMPTY. Each buffer starts with an 8-word header whose first u32 is the record
+ * count. `cap` = record capacity of each buffer (excluding the header): (cap+1)*8 u32 words. */
+#define PF_MIGRATE_WORDS 8
+int pf_migrate_pack(pf_handle* h, const pf_agents* a, uint32_t* up_buf, uint32_t* down_buf,
+                    int64_t cap, void* stream);
+/* Append the records of a received buffer into empty slots (lowest slot first, deterministic). */
+int pf_migrate_unpack(pf_handle* h, const pf_agents* a, const uint32_t* buf, int64_t cap,
+                      void* stream);
+
+int pf_counters_host(pf_handle* h, pf_counters* out_host, void* stream);
+int pf_counters_reset(pf_handle* h, void* stream);
+
+/* number of kernels this handle has launched (bench.py reports it as gpu_launches) */
+int pf_launch_count(const pf_handle* h, uint64_t* n);
+
+/* which stencil kernel variant pf_step_field uses: 0 = auto, 1 = register sliding window (LDG),
+ * 2 = TMA + mbarrier pipelined shared-memory tiles. For tuning sweeps. */
+int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHEROFIELD_H */

@@ -1,0 +1,471 @@
+// pf_agents.cuh — K2 (deterministic deposit) and K3 (sense -> decide -> move) kernels.
+#pragma once
+#include "pf_device.cuh"
+
+// ------------------------------------------------------------------------------------------
+// K2a: sort keys. key = local linear cell index ((ch*rows + lr)*W + col); agents that do not
+// deposit get the sentinel (= number of cells), which sorts behind every real key.
+// ------------------------------------------------------------------------------------------
+
+// Deposit rule of deposit_pheromone (reference sup:291-358): gate on has_moved (sup:308-310),
+// SEARCHING: counter+1, every `high_every`-th deposit is 20.0 else 1.0 (sup:312-318);
+// HOMING: 5.0 (sup:346-348). The counter lives in meta bits 8..31.
+__global__ void __launch_bounds__(256)
+k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
+                      const float* __restrict__ y, uint32_t* __restrict__ meta,
+                      uint32_t* __restrict__ keys, float* __restrict__ vals, uint32_t sentinel,
+                      unsigned long long* __restrict__ counters) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool dep = false;
+  if (i < n) {
+    uint32_t mt = meta[i];
+    uint32_t st = mt & PF_META_STATE_MASK;
+    uint32_t key = sentinel;
+    float amt = 0.0f;
+    if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && (mt & PF_META_MOVED)) {
+      uint32_t cnt = (mt >> PF_META_COUNT_SHIFT) + 1u;
+      amt = (st == PF_STATE_SEARCHING)
+                ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
+                : p.i_homing;
+      meta[i] = (mt & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
+      dep = true;
+      int r, q;
+      bool inside = pf_cell(p, x[i], y[i], r, q);
+      int ch = p.dep_ch[st];
+      if (inside && r >= p.row0 && r < p.row1)
+        key = (uint32_t)(((long long)ch * p.rows + (r - p.row0)) * p.W + q);
+    }
+    keys[i] = key;
+    vals[i] = amt;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, dep);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[1], (unsigned long long)__popc(m));
+}
+
+// generic positions/amounts (pf_deposit)
+__global__ void __launch_bounds__(256)
+k_deposit_keys_generic(PFDev p, long long n, const float* __restrict__ x,
+                       const float* __restrict__ y, const float* __restrict__ amount,
+                       const uint8_t* __restrict__ channel, uint32_t* __restrict__ keys,
+                       float* __restrict__ vals, uint32_t sentinel) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r, q;
+  bool inside = pf_cell(p, x[i], y[i], r, q);
+  int ch = channel ? (int)channel[i] : 0;
+  uint32_t key = sentinel;
+  if (inside && r >= p.row0 && r < p.row1 && ch < p.C)
+    key = (uint32_t)(((long long)ch * p.rows + (r - p.row0)) * p.W + q);
+  keys[i] = key;
+  vals[i] = amount[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: warp-aggregated segmented sum over the sorted (key, amount) pairs, in sorted (= agent)
+// order, one store per touched cell. A lane whose key differs from its predecessor's is a segment
+// head; heads add the following lanes' amounts one by one through shuffles (fixed order), and keep
+// reading global memory when the run continues past the warp. No atomics, no races: exactly one
+// thread writes each touched cell.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_deposit_segsum(PFDev p, long long n, const uint32_t* __restrict__ keys,
+                 const float* __restrict__ vals, uint32_t sentinel, float* __restrict__ field) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t key = sentinel;
+  float val = 0.0f;
+  if (i < n) {
+    key = keys[i];
+    val = vals[i];
+  }
+  uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+  if (lane == 0) prev = (i > 0 && i < n) ? keys[i - 1] : sentinel;
+  const bool head = (key != sentinel) && (i == 0 || key != prev);
+  float s = val;
+  bool open = head;  // still extending this head's run
+  for (int d = 1; d < 32; ++d) {
+    uint32_t nk = __shfl_down_sync(0xffffffffu, key, d);
+    float nv = __shfl_down_sync(0xffffffffu, val, d);
+    open = open && (lane + d < 32) && (nk == key);
+    if (open) s = fadd(s, nv);
+    if (!__any_sync(0xffffffffu, open)) break;
+  }
+  // the run reaches the end of the warp iff the last lane holds the same key: continue from
+  // global memory, still in sorted order
+  const uint32_t last_key = __shfl_sync(0xffffffffu, key, 31);
+  if (head && last_key == key) {
+    long long j = i - lane + 32;
+    while (j < n && keys[j] == key) {
+      s = fadd(s, vals[j]);
+      ++j;
+    }
+  }
+  if (head) {
+    const long long plane = (long long)p.rows * p.W;
+    const int ch = (int)(key / plane);
+    const long long rem = key - (long long)ch * plane;
+    const int lr = (int)(rem / p.W);
+    const int col = (int)(rem - (long long)lr * p.W);
+    float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
+    *cell = fadd(*cell, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: sense -> ordered arg-max -> PID -> wheel speeds -> diff-drive move, one thread per agent.
+// Mirrors oracle/pf_oracle.c po_agent_step_one op for op.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ int pf_nearest_food(const PFDev& p, float x, float y, float& d2_out) {
+  int best = 0;
+  float bd = 0.0f;
+  for (int k = 0; k < p.n_food; ++k) {
+    float dx = fsub(p.food_x[k], x);
+    float dy = fsub(p.food_y[k], y);
+    float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+    if (k == 0 || d2 < bd) {
+      bd = d2;
+      best = k;
+    }
+  }
+  d2_out = bd;
+  return best;
+}
+
+// the five DRUL values (reference sup:379-417 in dict order sup:390); NaN = direction absent
+__device__ __forceinline__ void pf_sense5(const PFDev& p, const float* __restrict__ f, float x,
+                                          float y, float theta, uint32_t st, float v[5]) {
+  const int ch = p.sen_ch[st & 3u];
+  float s = 0.0f, co = 1.0f;
+  if (p.sense_mode == PF_SENSE_HEADING) pf_sincos(theta, s, co);
+  int r0, q0;
+  pf_cell(p, x, y, r0, q0);
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    int r, q;
+    bool inside;
+    if (p.sense_mode == PF_SENSE_WORLD) {
+      r = r0 + p.drow[d];
+      q = q0 + p.dcol[d];
+      inside = (r >= 0 && r < p.H && q >= 0 && q < p.W);
+      if (d == PF_DIR_CURRENT) inside = true;
+    } else if (d == PF_DIR_CURRENT) {
+      r = r0;
+      q = q0;
+      inside = true;
+    } else {
+      float ux, uy;
+      if (d == PF_DIR_FRONT) { ux = co; uy = s; }
+      else if (d == PF_DIR_BACK) { ux = -co; uy = -s; }
+      else if (d == PF_DIR_LEFT) { ux = -s; uy = co; }
+      else { ux = s; uy = -co; }
+      float px = fadd(x, fmul(p.sense_dist, ux));
+      float py = fadd(y, fmul(p.sense_dist, uy));
+      inside = pf_cell(p, px, py, r, q);
+    }
+    if (inside && r >= p.row0 - 1 && r <= p.row1)
+      v[d] = __ldg(f + pf_addr(p, ch, r, q));
+    else
+      v[d] = __int_as_float(0x7fc00000);
+  }
+}
+
+__device__ __forceinline__ int pf_argmax5(const float v[5]) {
+  int dir = -1;
+  float best = 0.0f;
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    if (v[d] != v[d]) continue;
+    if (dir < 0 || v[d] > best) {
+      best = v[d];
+      dir = d;
+    }
+  }
+  return dir;
+}
+
+__global__ void __launch_bounds__(256)
+k_sense(PFDev p, const float* __restrict__ f, long long n, const float* __restrict__ x,
+        const float* __restrict__ y, const float* __restrict__ theta,
+        const uint32_t* __restrict__ meta, float* __restrict__ out5) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v[5];
+  uint32_t st = meta ? (meta[i] & PF_META_STATE_MASK) : PF_STATE_SEARCHING;
+  pf_sense5(p, f, x[i], y[i], theta ? theta[i] : 0.0f, st, v);
+#pragma unroll
+  for (int d = 0; d < 5; ++d) out5[i * 5 + d] = v[d];
+}
+
+// counters layout (unsigned long long): [0] ticks [1] deposits [2..7] decisions [8] grabbed
+// [9] delivered [10] migrated_out [11] migrated_in [12] migrate_dropped
+__global__ void __launch_bounds__(256)
+k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
+              float* __restrict__ ax, float* __restrict__ ay, float* __restrict__ ath,
+              float* __restrict__ awl, float* __restrict__ awr, uint32_t* __restrict__ ameta,
+              uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters) {
+  __shared__ unsigned int hist[8];
+  if (threadIdx.x < 8) hist[threadIdx.x] = 0;
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t mt = ameta[i];
+    uint32_t st = mt & PF_META_STATE_MASK;
+    if (st == PF_STATE_EMPTY) {
+      if (dec_out) dec_out[i] = PF_DEC_NONE;
+    } else {
+      float x = ax[i], y = ay[i], th = ath[i], wl = awl[i], wr = awr[i];
+      int dec = PF_DEC_NONE;
+      bool delivered = false;
+      if (st == PF_STATE_IDLE) {
+        wl = 0.0f;
+        wr = 0.0f;
+      } else if (!(flags & PF_STEP_SENSE)) {
+        wl = p.bl;  // Braitenberg base speeds only (reference sup:721-725, 736-744)
+        wr = p.br;
+      } else if (st == PF_STATE_SEARCHING) {
+        float v5[5];
+        pf_sense5(p, f, x, y, th, st, v5);
+        int dir = pf_argmax5(v5);
+        float d2;
+        int k = pf_nearest_food(p, x, y, d2);
+        float turn = pf_pid_turn(p, x, y, p.food_x[k], p.food_y[k]);
+        if (dir == PF_DIR_LEFT) {  // sup:455-458
+          float m = fsub(p.vmax, fabsf(turn));
+          wl = m > 0.0f ? m : 0.0f;
+          wr = p.vmax;
+          dec = PF_DEC_LEFT;
+        } else if (dir == PF_DIR_RIGHT) {  // sup:459-462
+          float m = fsub(p.vmax, fabsf(turn));
+          wr = m > 0.0f ? m : 0.0f;
+          wl = p.vmax;
+          dec = PF_DEC_RIGHT;
+        } else {  // sup:463-466
+          wl = p.cruise;
+          wr = p.cruise;
+          dec = PF_DEC_STRAIGHT;
+        }
+        wl = fadd(wl, p.bl);  // sup:468-470
+        wr = fadd(wr, p.br);
+      } else {  // HOMING, sup:475-514
+        float dx = fsub(p.nest_x, x);
+        float dy = fsub(p.nest_y, y);
+        float d = fsqrt(fadd(fmul(dx, dx), fmul(dy, dy)));
+        float dcm = rintf(fmul(d, 100.0f));
+        bool reached = (x == p.nest_x && y == p.nest_y) || (dcm >= p.home_lo && dcm <= p.home_hi);
+        if (!reached) {
+          float turn = pf_pid_turn(p, x, y, p.nest_x, p.nest_y);
+          if (d <= p.home_radius) {
+            float rt = rintf(fmul(turn, 100.0f));
+            if (rt > -200.0f && rt < 0.0f) {
+              wl = 0.0f;
+              wr = p.vmax;
+              dec = PF_DEC_LEFT;
+            } else if (rt < -200.0f) {
+              wr = 0.0f;
+              wl = p.vmax;
+              dec = PF_DEC_RIGHT;
+            } else {
+              dec = PF_DEC_KEEP;
+            }
+          } else {
+            wl = p.cruise;
+            wr = p.cruise;
+            dec = PF_DEC_STRAIGHT;
+          }
+          wl = fadd(wl, p.bl);
+          wr = fadd(wr, p.br);
+        } else {
+          wl = 0.0f;
+          wr = 0.0f;
+          dec = PF_DEC_STOP;
+          delivered = true;
+        }
+      }
+
+      uint32_t moved = mt & PF_META_MOVED;
+      if (flags & PF_STEP_MOVE) {
+        float v = fmul(fmul(p.wheel_r, fadd(wl, wr)), 0.5f);
+        float om = fdiv(fmul(p.wheel_r, fsub(wr, wl)), p.axle);
+        float nth = pf_wrap(fadd(th, fmul(om, p.dt)));
+        float sn, cs;
+        pf_sincos(nth, sn, cs);
+        float step = fmul(v, p.dt);
+        float nx = fadd(x, fmul(step, cs));
+        float ny = fadd(y, fmul(step, sn));
+        if (nx < p.xmin) {
+          nx = fadd(p.xmin, fsub(p.xmin, nx));
+          nth = pf_wrap(fsub(PF_PI_F, nth));
+        } else if (nx > p.xmax) {
+          nx = fsub(p.xmax, fsub(nx, p.xmax));
+          nth = pf_wrap(fsub(PF_PI_F, nth));
+        }
+        if (ny < p.ymin) {
+          ny = fadd(p.ymin, fsub(p.ymin, ny));
+          nth = -nth;
+        } else if (ny > p.ymax) {
+          ny = fsub(p.ymax, fsub(ny, p.ymax));
+          nth = -nth;
+        }
+        nx = fminf(fmaxf(nx, p.xmin), p.xmax);
+        ny = fminf(fmaxf(ny, p.ymin), p.ymax);
+        float ddx = fsub(nx, x), ddy = fsub(ny, y);
+        float dist = fsqrt(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
+        moved = (dist >= p.move_thr) ? PF_META_MOVED : 0u;  // has_moved, sup:263-273
+        x = nx;
+        y = ny;
+        th = nth;
+      }
+
+      uint32_t carry = mt & PF_META_CARRY;
+      if (p.fsm && (flags & PF_STEP_SENSE)) {
+        if (st == PF_STATE_SEARCHING) {
+          float d2;
+          pf_nearest_food(p, x, y, d2);
+          if (d2 <= p.food_r2) {
+            st = PF_STATE_HOMING;
+            carry = PF_META_CARRY;
+            atomicAdd(&hist[6], 1u);
+          }
+        } else if (st == PF_STATE_HOMING && delivered) {
+          st = PF_STATE_SEARCHING;
+          carry = 0;
+          atomicAdd(&hist[7], 1u);
+        }
+      }
+      atomicAdd(&hist[dec], 1u);
+      ax[i] = x;
+      ay[i] = y;
+      ath[i] = th;
+      awl[i] = wl;
+      awr[i] = wr;
+      ameta[i] = (mt & ~(PF_META_STATE_MASK | PF_META_MOVED | PF_META_DEC_MASK | PF_META_CARRY)) |
+                 st | moved | ((uint32_t)dec << PF_META_DEC_SHIFT) | carry;
+      if (dec_out) dec_out[i] = (uint8_t)dec;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && hist[threadIdx.x])
+    atomicAdd(&counters[2 + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// migration between row strips
+// ------------------------------------------------------------------------------------------
+constexpr int kMigWords = 8;  // u32 words per record and per header
+
+__global__ void __launch_bounds__(256)
+k_migrate_flags(PFDev p, long long n, const float* __restrict__ x, const float* __restrict__ y,
+                const uint32_t* __restrict__ meta, unsigned long long* __restrict__ flags) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long fl = 0ull;
+  if ((meta[i] & PF_META_STATE_MASK) != PF_STATE_EMPTY) {
+    int r, q;
+    pf_cell(p, x[i], y[i], r, q);
+    if (r < p.row0) fl = 1ull;
+    else if (r >= p.row1) fl = 1ull << 32;
+  }
+  flags[i] = fl;
+}
+
+__global__ void __launch_bounds__(256)
+k_migrate_scatter(long long n, long long cap, const unsigned long long* __restrict__ flags,
+                  const unsigned long long* __restrict__ ranks, float* ax, float* ay, float* ath,
+                  float* awl, float* awr, uint32_t* ameta, const uint32_t* __restrict__ agid,
+                  uint32_t* __restrict__ up, uint32_t* __restrict__ down,
+                  unsigned long long* __restrict__ counters) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long fl = flags[i], rk = ranks[i];
+  if (i == n - 1) {  // totals -> headers
+    unsigned long long tot = rk + fl;
+    unsigned long long nu = tot & 0xffffffffull, nd = tot >> 32;
+    unsigned long long su = nu < (unsigned long long)cap ? nu : cap;
+    unsigned long long sd = nd < (unsigned long long)cap ? nd : cap;
+    up[0] = (uint32_t)su;
+    down[0] = (uint32_t)sd;
+    atomicAdd(&counters[10], su + sd);
+    if (nu + nd > su + sd) atomicAdd(&counters[12], nu + nd - su - sd);
+  }
+  if (!fl) return;
+  uint32_t* dst;
+  unsigned long long r;
+  if (fl & 0xffffffffull) { dst = up; r = rk & 0xffffffffull; }
+  else { dst = down; r = rk >> 32; }
+  if (r >= (unsigned long long)cap) return;  // overflow: stays here, retried next tick
+  uint32_t* rec = dst + (r + 1) * kMigWords;
+  rec[0] = __float_as_uint(ax[i]);
+  rec[1] = __float_as_uint(ay[i]);
+  rec[2] = __float_as_uint(ath[i]);
+  rec[3] = __float_as_uint(awl[i]);
+  rec[4] = __float_as_uint(awr[i]);
+  rec[5] = ameta[i];
+  rec[6] = agid ? agid[i] : 0u;
+  rec[7] = 0u;
+  ameta[i] = PF_STATE_EMPTY;
+}
+
+__global__ void __launch_bounds__(256)
+k_empty_flags(long long n, const uint32_t* __restrict__ meta, unsigned long long* __restrict__ flags) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flags[i] = ((meta[i] & PF_META_STATE_MASK) == PF_STATE_EMPTY) ? 1ull : 0ull;
+}
+
+__global__ void __launch_bounds__(256)
+k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
+               const unsigned long long* __restrict__ ranks, const uint32_t* __restrict__ buf,
+               long long cap, float* ax, float* ay, float* ath, float* awl, float* awr,
+               uint32_t* ameta, uint32_t* agid, unsigned long long* __restrict__ counters) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long m = buf[0];
+  if (m > (unsigned long long)cap) m = cap;
+  if (i == n - 1) {
+    unsigned long long empties = ranks[i] + flags[i];
+    unsigned long long placed = m < empties ? m : empties;
+    atomicAdd(&counters[11], placed);
+    if (m > placed) atomicAdd(&counters[12], m - placed);
+  }
+  if (!flags[i]) return;
+  unsigned long long r = ranks[i];
+  if (r >= m) return;
+  const uint32_t* rec = buf + (r + 1) * kMigWords;
+  ax[i] = __uint_as_float(rec[0]);
+  ay[i] = __uint_as_float(rec[1]);
+  ath[i] = __uint_as_float(rec[2]);
+  awl[i] = __uint_as_float(rec[3]);
+  awr[i] = __uint_as_float(rec[4]);
+  ameta[i] = rec[5];
+  if (agid) agid[i] = rec[6];
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__global__ void k_fill_ghosts(PFDev p, float* f, int top, int bottom) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  int ch = blockIdx.y;
+  if (col >= p.W) return;
+  float* plane = f + (long long)ch * p.chan_stride;
+  if (top) plane[col] = plane[p.pitch + col];
+  if (bottom) plane[(long long)(p.rows + 1) * p.pitch + col] = plane[(long long)p.rows * p.pitch + col];
+}
+
+__global__ void k_fill(float* f, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) f[i] = v;
+}
+
+// I * exp(-rate * elapsed), fp64 (reference sup:519-525)
+__global__ void k_evaporate_trail(long long n, const double* __restrict__ elapsed,
+                                  const double* __restrict__ intensity, double rate,
+                                  double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = intensity[i] * exp(-rate * elapsed[i]);
+}
+
+__global__ void k_tick_counter(unsigned long long* counters) { counters[0] += 1ull; }

@@ -1,0 +1,201 @@
+// pf_stencil_tma.cuh — K1 variant 2: TMA bulk copies into an mbarrier-pipelined shared-memory ring.
+//
+// One CTA owns a strip of kTmaCols columns and streams the rows r0-1 .. r1 of its row block through
+// a ring of kStages stages x kStageRows rows. A single producer thread issues one
+// cp.async.bulk.shared.global (SASS UBLKCP) per row segment — (kTmaCols + 8) floats, 16 B aligned,
+// including 4 halo columns on each side — and arms the stage's `full` mbarrier with the byte count.
+// Eight consumer warps (128 columns each) wait on `full`, pull their float4 (LDS.128, conflict-free)
+// and the warp-edge scalar into registers, release the stage through the `empty` mbarrier, and run
+// the same register sliding window as k_stencil_rows; results go straight to HBM with STG.128.
+// Bytes in flight per SM are set by the ring depth, not by registers or occupancy.
+#pragma once
+#include "pf_stencil.cuh"
+
+constexpr int kTmaWarps = 8;                  // consumer warps
+constexpr int kTmaCols = kTmaWarps * 128;     // columns per CTA
+constexpr int kTmaRowFloats = kTmaCols + 8;   // + 4 halo floats each side
+constexpr int kTmaThreads = kTmaWarps * 32 + 32;  // + producer warp
+
+struct TmaStencilState {
+  bool attr_set[3][2];
+  char err[256];
+};
+
+static inline void tma_stencil_init(TmaStencilState* s) { memset(s, 0, sizeof(*s)); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int ST, int kStageRows, int kStages>
+__global__ void __launch_bounds__(kTmaThreads)
+k_stencil_tma(StencilArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * kStageRows * kTmaRowFloats);
+  uint64_t* empty = full + kStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.z;
+  const int c0 = blockIdx.x * kTmaCols;
+  const int r0 = a.r_begin + blockIdx.y * a.rows_per_cta;
+  const int r1 = min(a.r_end, r0 + a.rows_per_cta);
+  if (r0 >= r1) return;  // uniform per CTA
+  const int nstream = r1 - r0 + 2;  // rows r0-1 .. r1
+  const int niter = (nstream + kStageRows - 1) / kStageRows;
+
+  // columns copied per row: [g0, g1), placed so that global column c0-4 maps to ring offset 0
+  const int g0 = max(c0 - 4, 0);
+  const int g1 = (int)min((long long)c0 + kTmaCols + 4, a.pitch);
+  const uint32_t row_bytes = (uint32_t)(g1 - g0) * 4u;
+  const int dst_off = g0 - (c0 - 4);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTmaWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const float* __restrict__ base = a.cur + ch * a.chan_stride + a.pitch;
+
+  if (warp == kTmaWarps) {
+    // ===== producer: one elected lane =====
+    if (lane == 0) {
+      for (int it = 0; it < niter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int first = it * kStageRows;
+        const int cnt = min(kStageRows, nstream - first);
+        mbar_expect_tx(&full[s], row_bytes * (uint32_t)cnt);
+        for (int k = 0; k < cnt; ++k) {
+          int r = r0 - 1 + first + k;
+          r = max(a.row_lo, min(a.row_hi, r));
+          bulk_g2s(ring + ((size_t)s * kStageRows + k) * kTmaRowFloats + dst_off,
+                   base + (long long)r * a.pitch + g0, row_bytes, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int t = threadIdx.x;  // 0..255
+  int col4 = c0 + 4 * t;
+  const bool live = col4 < a.W;
+  const float keep = a.keep[ch], dk = a.dk[ch], thr = a.del_thr;
+  float* __restrict__ obase = a.nxt + ch * a.chan_stride + a.pitch;
+  const int my_off = 4 + 4 * t;  // ring offset of this thread's float4 within a row
+
+  RowQ qn, qc;
+  qn.v = make_float4(0.f, 0.f, 0.f, 0.f); qn.edge = 0.f;
+  qc = qn;
+  float nw = 0.f, ne = 0.f, cw = 0.f, ce = 0.f;
+
+  for (int it = 0; it < niter; ++it) {
+    const int s = it % kStages;
+    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+    mbar_wait(&full[s], ph);
+    const int first = it * kStageRows;
+    const int cnt = min(kStageRows, nstream - first);
+    RowQ rows[kStageRows];
+#pragma unroll
+    for (int k = 0; k < kStageRows; ++k) {
+      if (k < cnt) {
+        const float* rp = ring + ((size_t)s * kStageRows + k) * kTmaRowFloats;
+        rows[k].v = *reinterpret_cast<const float4*>(rp + my_off);
+        rows[k].edge = 0.f;
+        if (lane == 0) rows[k].edge = rp[my_off - 1];
+        if (lane == 31) rows[k].edge = rp[my_off + 4];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+    for (int k = 0; k < kStageRows; ++k) {
+      if (k < cnt) {
+        const int si = first + k;  // stream index; stream row = r0 - 1 + si
+        float sw, se;
+        row_we(rows[k], live ? col4 : a.W - 4, a.W, lane, sw, se);
+        if (si >= 2) {
+          const int rr = r0 + si - 2;
+          float4 o = stencil_vec<ST>(qn.v, qc.v, rows[k].v, cw, ce, nw, ne, sw, se, keep, dk, thr);
+          if (live) *reinterpret_cast<float4*>(obase + (long long)rr * a.pitch + col4) = o;
+        }
+        qn = qc; qc = rows[k];
+        nw = cw; ne = ce;
+        cw = sw; ce = se;
+      }
+    }
+  }
+}
+
+template <int ST, int R, int S>
+static int tma_launch_one(TmaStencilState* st, int slot, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+  const size_t smem = (size_t)S * R * kTmaRowFloats * sizeof(float) + 2 * S * sizeof(uint64_t);
+  const int sti = ST == 0 ? 0 : (ST == 5 ? 1 : 2);
+  if (!st->attr_set[sti][slot]) {
+    cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<ST, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      snprintf(st->err, sizeof(st->err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PF_ECUDA;
+    }
+    st->attr_set[sti][slot] = true;
+  }
+  k_stencil_tma<ST, R, S><<<grid, kTmaThreads, smem, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(st->err, sizeof(st->err), "launch: %s", cudaGetErrorString(e));
+    return PF_ECUDA;
+  }
+  return PF_OK;
+}
+
+// rows_per_cta <= 0 selects the default. Returns PF_ESTATE when the shape is not supported
+// (the caller then uses the register sliding-window kernel).
+static int tma_stencil_launch(TmaStencilState* st, const pf_config& cfg, const PFDev& d, StencilArgs a,
+                              int rows_per_cta, cudaStream_t s) {
+  (void)cfg;
+  if (d.W % 4 != 0 || d.W < 128) return PF_ESTATE;
+  const int nrows = a.r_end - a.r_begin;
+  int rpc = rows_per_cta > 0 ? rows_per_cta : 128;
+  if (rpc > nrows) rpc = nrows;
+  a.rows_per_cta = rpc;
+  dim3 grid((d.W + kTmaCols - 1) / kTmaCols, (nrows + rpc - 1) / rpc, d.C);
+  if (d.stencil == 0) return tma_launch_one<0, 4, 4>(st, 0, a, grid, s);
+  if (d.stencil == 5) return tma_launch_one<5, 4, 4>(st, 0, a, grid, s);
+  return tma_launch_one<9, 4, 4>(st, 0, a, grid, s);
+}

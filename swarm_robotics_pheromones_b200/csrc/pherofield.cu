@@ -1,0 +1,701 @@
+// pherofield.cu — the C-ABI library (include/pherofield.h) over the sm_100a kernels.
+//
+// Layout in HBM: two buffers (current / next), each [C][rows + 2][pitch] fp32, pitch = W rounded up
+// to 32 floats. Local row r of channel c lives at buf + c*chan_stride + (r+1)*pitch; rows -1 and
+// `rows` are ghost rows (neighbour strip's edge row, filled by the halo exchange; unused at the
+// arena's outer edges where the stencil clamps = reflect).
+#include <cub/cub.cuh>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/pherofield.h"
+#include "pf_agents.cuh"
+#include "pf_device.cuh"
+#include "pf_stencil.cuh"
+#include "pf_stencil_tma.cuh"
+
+static char g_create_err[512] = "";
+
+struct pf_handle {
+  pf_config cfg;
+  PFDev dev;
+  float* buf[2];
+  int cur;
+  long long buf_elems;
+  // scratch for sort / scan
+  long long cap;
+  char* scratch;  // 16 B per agent: keys_in, keys_out, vals_in, vals_out (or 2 x u64 for scans)
+  void* cub_temp;
+  size_t cub_temp_bytes;
+  int key_bits;
+  uint32_t sentinel;
+  unsigned long long* counters;  // device, 16 entries
+  double* d_sum;
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  uint64_t launches;
+  double t0, start_delay;
+  uint64_t ticks;
+  int variant, rows_per_cta;
+  TmaStencilState tma;
+  char err[512];
+};
+
+static int set_err(pf_handle* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PF_CUDA(h, call)                                                                  \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return set_err(h, PF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                     __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define PF_LAUNCH_CHECK(h)                                                          \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess)                                                         \
+      return set_err(h, PF_ECUDA, "kernel launch failed: %s (%s:%d)",               \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                  \
+    (h)->launches++;                                                                \
+  } while (0)
+
+static inline unsigned blocks_for(long long n, int threads) {
+  return (unsigned)((n + threads - 1) / threads);
+}
+
+static int ceil_log2_u64(unsigned long long v) {
+  int b = 0;
+  while ((1ull << b) < v) ++b;
+  return b < 1 ? 1 : b;
+}
+
+extern "C" int pf_abi_version(void) { return PF_ABI_VERSION; }
+
+extern "C" int pf_config_default(pf_config* c, int32_t H, int32_t W, int32_t C) {
+  if (!c || H <= 0 || W <= 0 || C <= 0 || C > PF_MAX_CHANNELS) return PF_EINVAL;
+  memset(c, 0, sizeof(*c));
+  c->abi_version = PF_ABI_VERSION;
+  c->device = 0;
+  c->H = H; c->W = W; c->C = C;
+  c->row0 = 0; c->row1 = H;
+  c->cell_size = 0.01f;
+  c->origin_x = 0.0f; c->origin_y = 0.0f;
+  c->stencil = 0;
+  for (int k = 0; k < PF_MAX_CHANNELS; ++k) {
+    c->evap_keep[k] = (float)(1.0 - 0.1);  // reference algo:248,356
+    c->diffusion[k] = 0.0f;
+  }
+  c->delete_threshold = 0.0f;
+  c->intensity_explore = 1.0f;   // sup:232
+  c->intensity_high = 20.0f;     // sup:233
+  c->intensity_homing = 5.0f;    // sup:234
+  c->high_every = 3;             // sup:316
+  c->move_threshold = 0.0015f;   // sup:260
+  if (C >= 2) {
+    c->deposit_channel[PF_STATE_SEARCHING] = 0;
+    c->deposit_channel[PF_STATE_HOMING] = 1;
+    c->sense_channel[PF_STATE_SEARCHING] = 1;
+    c->sense_channel[PF_STATE_HOMING] = 0;
+  }
+  c->sense_mode = PF_SENSE_HEADING;
+  const int drow[5] = {0, 0, 0, -1, 1}, dcol[5] = {0, 1, -1, 0, 0};
+  for (int d = 0; d < 5; ++d) { c->sense_drow[d] = drow[d]; c->sense_dcol[d] = dcol[d]; }
+  c->sense_dist = c->cell_size;
+  c->pid_kp = 1.0f; c->pid_kd = 0.01f;  // sup:437
+  c->cruise_speed = 1.0f;               // sup:197
+  c->max_speed = 3.14f;                 // sup:74
+  // sum_j coeff[j][i] * (1 - 0/512), accumulated in the order of sup:468-470
+  const double coeff[8][2] = {{0.942, -0.22}, {0.63, -0.1}, {0.5, -0.06}, {-0.06, -0.06},
+                              {-0.06, -0.06}, {-0.06, 0.5}, {-0.19, 0.63}, {-0.13, 0.942}};
+  double bl = 0.0, br = 0.0;
+  for (int j = 0; j < 8; ++j) { bl += coeff[j][0] * (1.0 - (0.0 / (1024 / 2))); br += coeff[j][1] * (1.0 - (0.0 / (1024 / 2))); }
+  c->braitenberg_l = (float)bl; c->braitenberg_r = (float)br;
+  c->home_radius = 0.7f; c->home_lo_cm = 5.0f; c->home_hi_cm = 6.0f;  // sup:489,667
+  c->nest_x = (float)(0.5 * H * 0.01); c->nest_y = (float)(0.5 * W * 0.01);
+  c->n_food = 1;
+  c->food_x[0] = (float)(0.75 * H * 0.01); c->food_y[0] = (float)(0.75 * W * 0.01);
+  c->food_radius = 0.05f;
+  c->fsm = 0;
+  c->dt = 0.064f;
+  c->wheel_radius = 0.02f; // E-puck.proto:100
+  c->axle_length = 0.052f; // E-puck.proto:86
+  return PF_OK;
+}
+
+static int validate(const pf_config* c) {
+  if (c->abi_version != PF_ABI_VERSION) return set_err(nullptr, PF_EINVAL, "abi_version %d != %d", c->abi_version, PF_ABI_VERSION);
+  if (c->H <= 0 || c->W <= 0 || c->C <= 0 || c->C > PF_MAX_CHANNELS) return set_err(nullptr, PF_EINVAL, "bad H/W/C");
+  if (c->row0 < 0 || c->row1 > c->H || c->row0 >= c->row1) return set_err(nullptr, PF_EINVAL, "bad strip [%d,%d)", c->row0, c->row1);
+  if (!(c->cell_size > 0.0f)) return set_err(nullptr, PF_EINVAL, "cell_size must be > 0");
+  if (c->stencil != 0 && c->stencil != 5 && c->stencil != 9) return set_err(nullptr, PF_EINVAL, "stencil must be 0, 5 or 9");
+  if (c->high_every <= 0) return set_err(nullptr, PF_EINVAL, "high_every must be > 0");
+  if (c->n_food < 1 || c->n_food > PF_MAX_FOOD) return set_err(nullptr, PF_EINVAL, "n_food out of range");
+  for (int s = 0; s < 4; ++s)
+    if (c->deposit_channel[s] < 0 || c->deposit_channel[s] >= c->C || c->sense_channel[s] < 0 || c->sense_channel[s] >= c->C)
+      return set_err(nullptr, PF_EINVAL, "channel routing out of range");
+  if (c->sense_mode != PF_SENSE_WORLD && c->sense_mode != PF_SENSE_HEADING) return set_err(nullptr, PF_EINVAL, "bad sense_mode");
+  if (c->sense_drow[0] != 0 || c->sense_dcol[0] != 0) return set_err(nullptr, PF_EINVAL, "the 'current' sense offset must be (0,0)");
+  bool sharded = c->row0 > 0 || c->row1 < c->H;
+  if (sharded) {  // ghost depth is one row
+    if (c->sense_mode == PF_SENSE_WORLD) {
+      for (int d = 0; d < 5; ++d)
+        if (c->sense_drow[d] < -1 || c->sense_drow[d] > 1) return set_err(nullptr, PF_EINVAL, "sharded field: |sense_drow| must be <= 1");
+    } else if (c->sense_dist > c->cell_size) {
+      return set_err(nullptr, PF_EINVAL, "sharded field: sense_dist must be <= cell_size");
+    }
+  }
+  unsigned long long cells = (unsigned long long)c->C * (unsigned long long)(c->row1 - c->row0) * (unsigned long long)c->W;
+  if (cells >= 0xffffffffull) return set_err(nullptr, PF_EINVAL, "more than 2^32-1 cells per handle: shard the field");
+  return PF_OK;
+}
+
+static void derive(pf_handle* h) {
+  const pf_config& c = h->cfg;
+  PFDev& d = h->dev;
+  d.H = c.H; d.W = c.W; d.C = c.C; d.row0 = c.row0; d.row1 = c.row1; d.rows = c.row1 - c.row0;
+  d.pitch = ((long long)c.W + 31) / 32 * 32;
+  d.chan_stride = (long long)(d.rows + 2) * d.pitch;
+  d.ox = c.origin_x; d.oy = c.origin_y;
+  d.inv_cs = 1.0f / c.cell_size;
+  d.xmin = c.origin_x; d.ymin = c.origin_y;
+  d.xmax = c.origin_x + (float)c.H * c.cell_size;
+  d.ymax = c.origin_y + (float)c.W * c.cell_size;
+  d.stencil = c.stencil;
+  for (int k = 0; k < PF_MAX_CHANNELS; ++k) {
+    d.keep[k] = c.evap_keep[k];
+    d.dk[k] = (c.stencil == 9) ? c.diffusion[k] / 6.0f : c.diffusion[k];
+  }
+  d.del_thr = c.delete_threshold;
+  d.i_explore = c.intensity_explore; d.i_high = c.intensity_high; d.i_homing = c.intensity_homing;
+  d.high_every = (unsigned)c.high_every;
+  d.move_thr = c.move_threshold;
+  for (int s = 0; s < 4; ++s) { d.dep_ch[s] = c.deposit_channel[s]; d.sen_ch[s] = c.sense_channel[s]; }
+  d.sense_mode = c.sense_mode;
+  for (int k = 0; k < 5; ++k) { d.drow[k] = c.sense_drow[k]; d.dcol[k] = c.sense_dcol[k]; }
+  d.sense_dist = c.sense_dist;
+  d.kp = c.pid_kp; d.kd = c.pid_kd; d.cruise = c.cruise_speed; d.vmax = c.max_speed;
+  d.bl = c.braitenberg_l; d.br = c.braitenberg_r;
+  d.home_radius = c.home_radius; d.home_lo = c.home_lo_cm; d.home_hi = c.home_hi_cm;
+  d.nest_x = c.nest_x; d.nest_y = c.nest_y;
+  d.n_food = c.n_food;
+  for (int k = 0; k < PF_MAX_FOOD; ++k) { d.food_x[k] = c.food_x[k]; d.food_y[k] = c.food_y[k]; }
+  d.food_r2 = c.food_radius * c.food_radius;
+  d.fsm = c.fsm;
+  d.dt = c.dt; d.wheel_r = c.wheel_radius; d.axle = c.axle_length;
+  h->buf_elems = (long long)c.C * d.chan_stride;
+  unsigned long long cells = (unsigned long long)c.C * d.rows * c.W;
+  h->sentinel = (uint32_t)cells;
+  h->key_bits = ceil_log2_u64(cells + 1);
+}
+
+extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
+  if (!cfg || !out) return set_err(nullptr, PF_EINVAL, "null argument");
+  int rc = validate(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_err(nullptr, PF_ECUDA, "no CUDA device (%s): pherofield has no CPU fallback",
+                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return set_err(nullptr, PF_EINVAL, "device %d of %d", cfg->device, ndev);
+  pf_handle* h = new (std::nothrow) pf_handle();
+  if (!h) return set_err(nullptr, PF_ENOMEM, "host allocation failed");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  derive(h);
+#define CREATE_CUDA(call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      set_err(nullptr, e__ == cudaErrorMemoryAllocation ? PF_ENOMEM : PF_ECUDA, "%s: %s", #call, \
+              cudaGetErrorString(e__));                                                    \
+      pf_destroy(h);                                                                       \
+      return e__ == cudaErrorMemoryAllocation ? PF_ENOMEM : PF_ECUDA;                      \
+    }                                                                                      \
+  } while (0)
+  CREATE_CUDA(cudaSetDevice(cfg->device));
+  CREATE_CUDA(cudaMalloc(&h->buf[0], sizeof(float) * h->buf_elems));
+  CREATE_CUDA(cudaMalloc(&h->buf[1], sizeof(float) * h->buf_elems));
+  CREATE_CUDA(cudaMemset(h->buf[0], 0, sizeof(float) * h->buf_elems));
+  CREATE_CUDA(cudaMemset(h->buf[1], 0, sizeof(float) * h->buf_elems));
+  CREATE_CUDA(cudaMalloc(&h->counters, sizeof(unsigned long long) * 16));
+  CREATE_CUDA(cudaMemset(h->counters, 0, sizeof(unsigned long long) * 16));
+  CREATE_CUDA(cudaMalloc(&h->d_sum, sizeof(double)));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CREATE_CUDA(cudaDeviceSynchronize());
+#undef CREATE_CUDA
+  h->variant = 0;
+  h->rows_per_cta = 0;
+  tma_stencil_init(&h->tma);
+  *out = h;
+  return PF_OK;
+}
+
+extern "C" int pf_destroy(pf_handle* h) {
+  if (!h) return PF_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  if (h->buf[0]) cudaFree(h->buf[0]);
+  if (h->buf[1]) cudaFree(h->buf[1]);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->cub_temp) cudaFree(h->cub_temp);
+  if (h->counters) cudaFree(h->counters);
+  if (h->d_sum) cudaFree(h->d_sum);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  delete h;
+  return PF_OK;
+}
+
+extern "C" const char* pf_last_error(const pf_handle* h) { return h ? h->err : g_create_err; }
+
+extern "C" int pf_get_config(const pf_handle* h, pf_config* out) {
+  if (!h || !out) return PF_EINVAL;
+  *out = h->cfg;
+  return PF_OK;
+}
+
+extern "C" int pf_reserve_agents(pf_handle* h, int64_t max_agents) {
+  if (!h || max_agents < 0) return PF_EINVAL;
+  if (max_agents <= h->cap) return PF_OK;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  PF_CUDA(h, cudaDeviceSynchronize());
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->cub_temp) cudaFree(h->cub_temp);
+  h->scratch = nullptr; h->cub_temp = nullptr; h->cap = 0;
+  long long cap = (max_agents + 1023) / 1024 * 1024;
+  PF_CUDA(h, cudaMalloc(&h->scratch, (size_t)cap * 16));
+  size_t sort_bytes = 0, scan_bytes = 0;
+  PF_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                             (const float*)nullptr, (float*)nullptr, (int)cap, 0, 32, (cudaStream_t)0));
+  PF_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const unsigned long long*)nullptr,
+                                           (unsigned long long*)nullptr, (int)cap, (cudaStream_t)0));
+  h->cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  PF_CUDA(h, cudaMalloc(&h->cub_temp, h->cub_temp_bytes));
+  h->cap = cap;
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// field access
+// ---------------------------------------------------------------------------------------------
+extern "C" int pf_field_ptr(pf_handle* h, int which, int channel, float** ptr, int64_t* pitch) {
+  if (!h || !ptr || channel < 0 || channel >= h->cfg.C || (which != 0 && which != 1)) return PF_EINVAL;
+  float* b = h->buf[which ? (h->cur ^ 1) : h->cur];
+  *ptr = b + (long long)channel * h->dev.chan_stride + h->dev.pitch;
+  if (pitch) *pitch = h->dev.pitch;
+  return PF_OK;
+}
+
+extern "C" int pf_field_fill(pf_handle* h, int channel, float value, void* stream) {
+  if (!h || channel < -1 || channel >= h->cfg.C) return PF_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  float* b = h->buf[h->cur];
+  long long n = channel < 0 ? h->buf_elems : h->dev.chan_stride;
+  if (channel >= 0) b += (long long)channel * h->dev.chan_stride;
+  k_fill<<<592, 256, 0, s>>>(b, n, value);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+extern "C" int pf_field_upload_host(pf_handle* h, int channel, const float* src, void* stream) {
+  if (!h || !src || channel < 0 || channel >= h->cfg.C) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  float* dst = h->buf[h->cur] + (long long)channel * h->dev.chan_stride + h->dev.pitch;
+  PF_CUDA(h, cudaMemcpy2DAsync(dst, sizeof(float) * h->dev.pitch, src, sizeof(float) * h->cfg.W,
+                               sizeof(float) * h->cfg.W, h->dev.rows, cudaMemcpyHostToDevice,
+                               (cudaStream_t)stream));
+  return PF_OK;
+}
+
+extern "C" int pf_snapshot_host(pf_handle* h, int channel, float* dst, void* stream) {
+  if (!h || !dst || channel < 0 || channel >= h->cfg.C) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  const float* src = h->buf[h->cur] + (long long)channel * h->dev.chan_stride + h->dev.pitch;
+  PF_CUDA(h, cudaMemcpy2DAsync(dst, sizeof(float) * h->cfg.W, src, sizeof(float) * h->dev.pitch,
+                               sizeof(float) * h->cfg.W, h->dev.rows, cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+  PF_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return PF_OK;
+}
+
+extern "C" int pf_fill_ghosts(pf_handle* h, void* stream) {
+  if (!h) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  int top = h->cfg.row0 == 0, bottom = h->cfg.row1 == h->cfg.H;
+  if (!top && !bottom) return PF_OK;
+  dim3 grid(blocks_for(h->cfg.W, 256), h->cfg.C);
+  k_fill_ghosts<<<grid, 256, 0, (cudaStream_t)stream>>>(h->dev, h->buf[h->cur], top, bottom);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+struct RowSumOp {
+  const float* base;
+  long long pitch;
+  int W;
+  __device__ double operator()(long long k) const {
+    long long r = k / W;
+    int c = (int)(k - r * W);
+    return (double)base[r * pitch + c];
+  }
+};
+
+extern "C" int pf_field_sum_host(pf_handle* h, int channel, double* sum_host, void* stream) {
+  if (!h || !sum_host || channel < 0 || channel >= h->cfg.C) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  RowSumOp op{h->buf[h->cur] + (long long)channel * h->dev.chan_stride + h->dev.pitch, h->dev.pitch, h->cfg.W};
+  cub::CountingInputIterator<long long> cnt(0);
+  cub::TransformInputIterator<double, RowSumOp, cub::CountingInputIterator<long long>> it(cnt, op);
+  long long n = (long long)h->dev.rows * h->cfg.W;
+  if (n > 0x7fffffffll) return set_err(h, PF_EINVAL, "pf_field_sum_host: more than 2^31 cells per channel");
+  size_t bytes = 0;
+  PF_CUDA(h, cub::DeviceReduce::Sum(nullptr, bytes, it, h->d_sum, (int)n, s));
+  void* tmp = nullptr;
+  PF_CUDA(h, cudaMallocAsync(&tmp, bytes, s));
+  PF_CUDA(h, cub::DeviceReduce::Sum(tmp, bytes, it, h->d_sum, (int)n, s));
+  PF_CUDA(h, cudaFreeAsync(tmp, s));
+  PF_CUDA(h, cudaMemcpyAsync(sum_host, h->d_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
+  PF_CUDA(h, cudaStreamSynchronize(s));
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 launch
+// ---------------------------------------------------------------------------------------------
+static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) {
+  if (r_begin >= r_end) return PF_OK;
+  const PFDev& d = h->dev;
+  StencilArgs a;
+  a.cur = h->buf[h->cur];
+  a.nxt = h->buf[h->cur ^ 1];
+  a.W = d.W; a.rows = d.rows; a.pitch = d.pitch; a.chan_stride = d.chan_stride;
+  a.r_begin = r_begin; a.r_end = r_end;
+  a.row_lo = (h->cfg.row0 == 0) ? 0 : -1;
+  a.row_hi = (h->cfg.row1 == h->cfg.H) ? d.rows - 1 : d.rows;
+  for (int k = 0; k < PF_MAX_CHANNELS; ++k) { a.keep[k] = d.keep[k]; a.dk[k] = d.dk[k]; }
+  a.del_thr = d.del_thr;
+  const int nrows = r_end - r_begin;
+  if (d.W % 4 != 0) {
+    dim3 grid(blocks_for(d.W, 256), nrows, d.C);
+    if (d.stencil == 0) k_stencil_scalar<0><<<grid, 256, 0, s>>>(a);
+    else if (d.stencil == 5) k_stencil_scalar<5><<<grid, 256, 0, s>>>(a);
+    else k_stencil_scalar<9><<<grid, 256, 0, s>>>(a);
+    PF_LAUNCH_CHECK(h);
+    return PF_OK;
+  }
+  int variant = h->variant;
+  if (variant == 0) variant = 1;
+  if (variant == 2) {
+    int rc = tma_stencil_launch(&h->tma, h->cfg, d, a, h->rows_per_cta, s);
+    if (rc == PF_OK) { h->launches++; return PF_OK; }
+    if (rc != PF_ESTATE) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
+    // PF_ESTATE: shape not supported by the TMA variant -> register sliding window
+  }
+  int rpc = h->rows_per_cta;
+  const int xblocks = (d.W / 4 + kStencilThreads - 1) / kStencilThreads;
+  if (rpc <= 0) {
+    // aim for >= 8 waves of 148 SMs x 8 CTAs, at least 8 rows per CTA, at most 128
+    long long want = 148ll * 8 * 8;
+    long long chunks = want / ((long long)xblocks * d.C);
+    if (chunks < 1) chunks = 1;
+    rpc = (int)((nrows + chunks - 1) / chunks);
+    if (rpc < 8) rpc = 8;
+    if (rpc > 128) rpc = 128;
+  }
+  a.rows_per_cta = rpc;
+  dim3 grid(xblocks, (nrows + rpc - 1) / rpc, d.C);
+  if (d.stencil == 0) k_stencil_rows<0><<<grid, kStencilThreads, 0, s>>>(a);
+  else if (d.stencil == 5) k_stencil_rows<5><<<grid, kStencilThreads, 0, s>>>(a);
+  else k_stencil_rows<9><<<grid, kStencilThreads, 0, s>>>(a);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+static bool is_sharded(const pf_handle* h) { return h->cfg.row0 > 0 || h->cfg.row1 < h->cfg.H; }
+
+extern "C" int pf_step_field(pf_handle* h, int nsteps, void* stream) {
+  if (!h || nsteps < 0) return PF_EINVAL;
+  if (is_sharded(h) && nsteps > 1)
+    return set_err(h, PF_ESTATE, "sharded handle: one step per halo exchange (nsteps must be 1)");
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < nsteps; ++i) {
+    int rc = launch_stencil(h, 0, h->dev.rows, (cudaStream_t)stream);
+    if (rc) return rc;
+    h->cur ^= 1;
+  }
+  return PF_OK;
+}
+
+extern "C" int pf_step_field_rows(pf_handle* h, int row_begin, int row_end, void* stream) {
+  if (!h || row_begin < 0 || row_end > h->dev.rows) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  return launch_stencil(h, row_begin, row_end, (cudaStream_t)stream);
+}
+
+extern "C" int pf_swap(pf_handle* h) {
+  if (!h) return PF_EINVAL;
+  h->cur ^= 1;
+  return PF_OK;
+}
+
+extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_cta) {
+  if (!h || variant < 0 || variant > 2 || rows_per_cta < 0) return PF_EINVAL;
+  h->variant = variant;
+  h->rows_per_cta = rows_per_cta;
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 launch
+// ---------------------------------------------------------------------------------------------
+static int sort_and_sum(pf_handle* h, long long n, cudaStream_t s) {
+  uint32_t* keys_in = (uint32_t*)h->scratch;
+  uint32_t* keys_out = keys_in + h->cap;
+  float* vals_in = (float*)(keys_out + h->cap);
+  float* vals_out = vals_in + h->cap;
+  size_t bytes = h->cub_temp_bytes;
+  PF_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_temp, bytes, keys_in, keys_out, vals_in, vals_out,
+                                             (int)n, 0, h->key_bits, s));
+  k_deposit_segsum<<<blocks_for(n, 256), 256, 0, s>>>(h->dev, n, keys_out, vals_out, h->sentinel,
+                                                     h->buf[h->cur]);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+extern "C" int pf_deposit(pf_handle* h, int64_t n, const float* x, const float* y, const float* amount,
+                          const uint8_t* channel, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!x || !y || !amount))) return PF_EINVAL;
+  if (n == 0) return PF_OK;
+  if (n > 0x7fffffffll) return set_err(h, PF_EINVAL, "more than 2^31-1 deposits per call");
+  int rc = pf_reserve_agents(h, n);
+  if (rc) return rc;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t* keys_in = (uint32_t*)h->scratch;
+  float* vals_in = (float*)(keys_in + 2 * h->cap);
+  k_deposit_keys_generic<<<blocks_for(n, 256), 256, 0, s>>>(h->dev, n, x, y, amount, channel, keys_in,
+                                                           vals_in, h->sentinel);
+  PF_LAUNCH_CHECK(h);
+  return sort_and_sum(h, n, s);
+}
+
+static int check_agents(pf_handle* h, const pf_agents* a) {
+  if (!h || !a || a->n < 0) return PF_EINVAL;
+  if (a->n > 0 && (!a->x || !a->y || !a->theta || !a->wl || !a->wr || !a->meta))
+    return set_err(h, PF_EINVAL, "pf_agents has null arrays");
+  if (a->n > 0x7fffffffll) return set_err(h, PF_EINVAL, "more than 2^31-1 agent slots per handle");
+  return PF_OK;
+}
+
+extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (a->n == 0) return PF_OK;
+  rc = pf_reserve_agents(h, a->n);
+  if (rc) return rc;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t* keys_in = (uint32_t*)h->scratch;
+  float* vals_in = (float*)(keys_in + 2 * h->cap);
+  k_deposit_keys_agents<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, keys_in,
+                                                             vals_in, h->sentinel, h->counters);
+  PF_LAUNCH_CHECK(h);
+  return sort_and_sum(h, a->n, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 launch
+// ---------------------------------------------------------------------------------------------
+extern "C" int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y, const float* theta,
+                        const uint32_t* meta, float* out5, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!x || !y || !out5))) return PF_EINVAL;
+  if (h->cfg.sense_mode == PF_SENSE_HEADING && n > 0 && !theta)
+    return set_err(h, PF_EINVAL, "heading-relative sensing needs theta");
+  if (n == 0) return PF_OK;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_sense<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->dev, h->buf[h->cur], n, x, y, theta, meta, out5);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s) {
+  k_agents_step<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, h->buf[h->cur], flags, a->n, a->x, a->y,
+                                                     a->theta, a->wl, a->wr, a->meta, dec, h->counters);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+extern "C" int pf_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* decisions_out,
+                              void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (a->n == 0) return PF_OK;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  return launch_agents_step(h, a, flags, decisions_out, (cudaStream_t)stream);
+}
+
+extern "C" int pf_set_time(pf_handle* h, double time_s, double start_delay_s) {
+  if (!h) return PF_EINVAL;
+  h->t0 = time_s;
+  h->ticks = 0;
+  h->start_delay = start_delay_s;
+  return PF_OK;
+}
+
+extern "C" int pf_get_time(const pf_handle* h, double* time_s, uint64_t* ticks) {
+  if (!h) return PF_EINVAL;
+  if (time_s) *time_s = h->t0 + (double)h->ticks * (double)h->cfg.dt;
+  if (ticks) *ticks = h->ticks;
+  return PF_OK;
+}
+
+extern "C" int pf_step(pf_handle* h, const pf_agents* a, int nsteps, void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (nsteps < 0) return PF_EINVAL;
+  if (is_sharded(h)) return set_err(h, PF_ESTATE, "pf_step on a sharded handle: drive the phases from the host");
+  rc = pf_reserve_agents(h, a->n);
+  if (rc) return rc;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int t = 0; t < nsteps; ++t) {
+    const double now = h->t0 + (double)h->ticks * (double)h->cfg.dt;
+    const bool sense = now >= h->start_delay;
+    const uint32_t flags = PF_STEP_MOVE | (sense ? PF_STEP_SENSE : 0u);
+    if (sense && a->n > 0) {  // deposit_pheromone, sup:577
+      rc = pf_agents_deposit(h, a, stream);
+      if (rc) return rc;
+    }
+    // sense/decide/move (side stream) and evaporate+diffuse (main stream) both read the
+    // post-deposit field and write disjoint data: run them concurrently
+    if (a->n > 0) {
+      PF_CUDA(h, cudaEventRecord(h->ev_fork, s));
+      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      rc = launch_agents_step(h, a, flags, nullptr, h->side);
+      if (rc) return rc;
+      PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+    }
+    rc = launch_stencil(h, 0, h->dev.rows, s);
+    if (rc) return rc;
+    if (a->n > 0) PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    k_tick_counter<<<1, 1, 0, s>>>(h->counters);
+    PF_LAUNCH_CHECK(h);
+    h->cur ^= 1;
+    h->ticks++;
+  }
+  return PF_OK;
+}
+
+extern "C" int pf_evaporate_trail(pf_handle* h, int64_t n, const double* elapsed, const double* intensity,
+                                  double rate, double* out, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!elapsed || !intensity || !out))) return PF_EINVAL;
+  if (n == 0) return PF_OK;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_evaporate_trail<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, elapsed, intensity, rate, out);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// migration
+// ---------------------------------------------------------------------------------------------
+extern "C" int pf_migrate_pack(pf_handle* h, const pf_agents* a, uint32_t* up_buf, uint32_t* down_buf,
+                               int64_t cap, void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (!up_buf || !down_buf || cap < 0) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a->n == 0) {
+    PF_CUDA(h, cudaMemsetAsync(up_buf, 0, sizeof(uint32_t) * kMigWords, s));
+    PF_CUDA(h, cudaMemsetAsync(down_buf, 0, sizeof(uint32_t) * kMigWords, s));
+    return PF_OK;
+  }
+  rc = pf_reserve_agents(h, a->n);
+  if (rc) return rc;
+  unsigned long long* flags = (unsigned long long*)h->scratch;
+  unsigned long long* ranks = flags + h->cap;
+  k_migrate_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, flags);
+  PF_LAUNCH_CHECK(h);
+  size_t bytes = h->cub_temp_bytes;
+  PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
+  k_migrate_scatter<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, cap, flags, ranks, a->x, a->y, a->theta,
+                                                         a->wl, a->wr, a->meta, a->gid, up_buf, down_buf,
+                                                         h->counters);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+extern "C" int pf_migrate_unpack(pf_handle* h, const pf_agents* a, const uint32_t* buf, int64_t cap,
+                                 void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (!buf || cap < 0) return PF_EINVAL;
+  if (a->n == 0) return PF_OK;
+  rc = pf_reserve_agents(h, a->n);
+  if (rc) return rc;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* flags = (unsigned long long*)h->scratch;
+  unsigned long long* ranks = flags + h->cap;
+  k_empty_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, a->meta, flags);
+  PF_LAUNCH_CHECK(h);
+  size_t bytes = h->cub_temp_bytes;
+  PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
+  k_migrate_fill<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, flags, ranks, buf, cap, a->x, a->y, a->theta,
+                                                      a->wl, a->wr, a->meta, a->gid, h->counters);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// counters
+// ---------------------------------------------------------------------------------------------
+extern "C" int pf_counters_host(pf_handle* h, pf_counters* out, void* stream) {
+  if (!h || !out) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  unsigned long long c[16];
+  PF_CUDA(h, cudaMemcpyAsync(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PF_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  out->ticks = c[0];
+  out->deposits = c[1];
+  for (int k = 0; k < 6; ++k) out->decisions[k] = c[2 + k];
+  out->food_grabbed = c[8];
+  out->food_delivered = c[9];
+  out->migrated_out = c[10];
+  out->migrated_in = c[11];
+  out->migrate_dropped = c[12];
+  return PF_OK;
+}
+
+extern "C" int pf_counters_reset(pf_handle* h, void* stream) {
+  if (!h) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  PF_CUDA(h, cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long) * 16, (cudaStream_t)stream));
+  return PF_OK;
+}
+
+extern "C" int pf_launch_count(const pf_handle* h, uint64_t* n) {
+  if (!h || !n) return PF_EINVAL;
+  *n = h->launches;
+  return PF_OK;
+}

@@ -1,0 +1,393 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs. Integer/index work and (because op order is fixed and FMA-free) the fp32 field values are
+compared BIT-EXACT; the north_star tolerance for field values (1e-5 of max after 1000 steps) is
+asserted as well."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense
+from swarm_robotics_pheromones_b200 import abi
+from swarm_robotics_pheromones_b200.field import PheroField, Swarm
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_bitexact(a, b, what=""):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    assert a.shape == b.shape, what
+    bad = bits(a) != bits(b)
+    # +0 / -0 never arise on this path; NaNs compare by bit pattern class
+    bad &= ~(np.isnan(a) & np.isnan(b))
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} differ; first at {np.argwhere(bad)[:3].tolist()} " \
+                          f"gpu={a[bad][:3]} oracle={b[bad][:3]}"
+
+
+def make_cfg(H, W, C=1, stencil=5, D=0.1, **kw):
+    cfg = abi.default_config(H, W, C)
+    cfg.stencil = stencil
+    for k in range(C):
+        cfg.diffusion[k] = D * (1.0 + 0.5 * k)
+        cfg.evap_keep[k] = 0.9 + 0.03 * k
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def rand_agents(rng, cfg, n, margin=0.0, states=None):
+    xmax = cfg.H * cfg.cell_size
+    ymax = cfg.W * cfg.cell_size
+    x = rng.uniform(margin, xmax - margin, n).astype(np.float32)
+    y = rng.uniform(margin, ymax - margin, n).astype(np.float32)
+    th = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    st = abi.STATE_SEARCHING if states is None else states
+    return x, y, th, st
+
+
+# ----------------------------------------------------------------------------- K1 stencil
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("stencil", [0, 5, 9])
+@pytest.mark.parametrize("shape", [(64, 128, 1), (37, 256, 2), (130, 1024, 1), (96, 2176, 2), (33, 132, 1)])
+def test_stencil_bitexact(shape, stencil, variant):
+    H, W, C = shape
+    rng = np.random.default_rng(H * 1000 + W + stencil)
+    cfg = make_cfg(H, W, C, stencil)
+    f0 = rng.random((C, H, W), dtype=np.float32) * 10
+    o = dense.DenseOracle(cfg)
+    o.set_field(f0)
+    g = PheroField(cfg)
+    g.set_stencil_variant(variant, 16)
+    g.upload(f0)
+    o.step_field(7)
+    g.step_field(7)
+    assert_bitexact(g.snapshot(), o.field, f"stencil {stencil} {shape} v{variant}")
+    g.close()
+
+
+@pytest.mark.parametrize("stencil", [0, 5, 9])
+def test_stencil_odd_width_scalar_path(stencil):
+    # 497 x 495 is the heat-map of reference graph.py:10
+    cfg = make_cfg(497, 495, 1, stencil)
+    rng = np.random.default_rng(5)
+    f0 = rng.random((1, 497, 495), dtype=np.float32)
+    o = dense.DenseOracle(cfg)
+    o.set_field(f0)
+    g = PheroField(cfg)
+    g.upload(f0)
+    o.step_field(5)
+    g.step_field(5)
+    assert_bitexact(g.snapshot(), o.field)
+    g.close()
+
+
+def test_stencil_delete_threshold():
+    cfg = make_cfg(64, 256, 1, 5)
+    cfg.delete_threshold = 0.1  # sup:603
+    rng = np.random.default_rng(11)
+    f0 = (rng.random((1, 64, 256), dtype=np.float32) * 0.3).astype(np.float32)
+    o = dense.DenseOracle(cfg)
+    o.set_field(f0)
+    g = PheroField(cfg)
+    g.upload(f0)
+    o.step_field(6)
+    g.step_field(6)
+    assert (o.field == 0).any()
+    assert_bitexact(g.snapshot(), o.field)
+    g.close()
+
+
+def test_stencil_mass_conservation_large():
+    # size-independent property at a size the oracle would not finish quickly: with keep = 1 the
+    # reflect-boundary Laplacian conserves the total (graph.py: sum stays 15200)
+    H = W = 4096
+    cfg = make_cfg(H, W, 1, 9, D=0.15)
+    cfg.evap_keep[0] = 1.0
+    g = PheroField(cfg)
+    v = g.view()
+    torch.manual_seed(0)
+    v.copy_(torch.rand((1, H, W), device="cuda"))
+    s0 = g.total(0)
+    g.step_field(20)
+    s1 = g.total(0)
+    assert abs(s1 - s0) / s0 < 1e-6
+    # and pure evaporation scales the total by keep^n
+    cfg2 = make_cfg(H, W, 1, 0)
+    cfg2.evap_keep[0] = 0.9
+    g2 = PheroField(cfg2)
+    g2.view().copy_(g.view())
+    g2.step_field(3)
+    assert abs(g2.total(0) / s1 - 0.9 ** 3) < 1e-5
+    g.close()
+    g2.close()
+
+
+# ----------------------------------------------------------------------------- K2 deposit
+@pytest.mark.parametrize("C", [1, 2])
+def test_deposit_generic_bitexact(C):
+    cfg = make_cfg(96, 160, C, 5)
+    rng = np.random.default_rng(21)
+    n = 20000
+    x = rng.uniform(-0.05, cfg.H * cfg.cell_size + 0.05, n).astype(np.float32)  # some outside
+    y = rng.uniform(-0.05, cfg.W * cfg.cell_size + 0.05, n).astype(np.float32)
+    # hot cells: many agents in one cell, long runs crossing warp boundaries
+    x[:3000] = 0.335
+    y[:3000] = 0.777
+    x[3000:3100] = 0.0
+    y[3000:3100] = 0.0
+    amount = rng.random(n, dtype=np.float32) * 3  # arbitrary fp32: order matters
+    ch = rng.integers(0, C, n).astype(np.uint8)
+    f0 = rng.random((C, 96, 160), dtype=np.float32)
+    o = dense.DenseOracle(cfg)
+    o.set_field(f0)
+    o.deposit(x, y, amount, ch)
+    g = PheroField(cfg)
+    g.upload(f0)
+    g.deposit(torch.tensor(x).cuda(), torch.tensor(y).cuda(), torch.tensor(amount).cuda(),
+              torch.tensor(ch).cuda())
+    assert_bitexact(g.snapshot(), o.field, "generic deposit")
+    g.close()
+
+
+def test_deposit_empty_and_all_outside():
+    cfg = make_cfg(32, 64, 1, 0)
+    g = PheroField(cfg)
+    e = torch.empty(0, device="cuda")
+    g.deposit(e, e, e)
+    x = torch.full((100,), -1.0, device="cuda")
+    g.deposit(x, x, torch.ones(100, device="cuda"))
+    assert g.total(0) == 0.0
+    g.close()
+
+
+def test_agents_deposit_rule():
+    # every-3rd rule on the agent's own counter (sup:316-318), homing amount, moved gate
+    cfg = make_cfg(64, 64, 2, 0)
+    rng = np.random.default_rng(3)
+    n = 5000
+    x, y, th, _ = rand_agents(rng, cfg, n)
+    st = rng.integers(1, 4, n)
+    a_np = dense.AgentsNP(x, y, th, st)
+    a_np.meta[::7] &= ~np.uint32(abi.META_MOVED)
+    a_np.meta |= (rng.integers(0, 50, n).astype(np.uint32) << abi.META_COUNT_SHIFT)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    sw = Swarm(x, y, th, st)
+    sw.load_numpy({f: getattr(a_np, f) for f in a_np.FIELDS})
+    for _ in range(4):
+        o.agents_deposit(a_np)
+        g.agents_deposit(sw)
+    got = sw.to_numpy()
+    assert (got["meta"] == a_np.meta).all()
+    assert_bitexact(g.snapshot(), o.field)
+    assert g.counters().deposits == int(o.counters[8])
+    g.close()
+
+
+# ----------------------------------------------------------------------------- K3 sense/decide/move
+@pytest.mark.parametrize("mode", [abi.SENSE_WORLD, abi.SENSE_HEADING])
+def test_sense_bitexact(mode):
+    cfg = make_cfg(80, 96, 2, 5)
+    cfg.sense_mode = mode
+    rng = np.random.default_rng(8)
+    f0 = rng.random((2, 80, 96), dtype=np.float32)
+    n = 4000
+    x, y, th, _ = rand_agents(rng, cfg, n)
+    x[:50] = 0.0  # wall-hugging agents: absent directions
+    y[50:100] = cfg.W * cfg.cell_size
+    st = rng.integers(1, 3, n)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    o.set_field(f0)
+    g = PheroField(cfg)
+    g.upload(f0)
+    sw = Swarm(x, y, th, st)
+    want = o.sense(a_np.x, a_np.y, a_np.theta, a_np.meta)
+    got = g.sense(sw.x, sw.y, sw.theta, sw.meta).cpu().numpy()
+    assert np.isnan(want).any()
+    assert (np.isnan(want) == np.isnan(got)).all()
+    assert_bitexact(got, want)
+    g.close()
+
+
+def _compare_agents(sw, a_np, what=""):
+    got = sw.to_numpy()
+    for f in ("meta", "gid"):
+        assert (got[f] == getattr(a_np, f)).all(), f"{what}: {f} differs"
+    for f in ("x", "y", "theta", "wl", "wr"):
+        assert_bitexact(got[f], getattr(a_np, f), f"{what}: {f}")
+
+
+@pytest.mark.parametrize("mode", [abi.SENSE_WORLD, abi.SENSE_HEADING])
+def test_agents_step_bitexact(mode):
+    cfg = make_cfg(128, 128, 1, 5)
+    cfg.sense_mode = mode
+    cfg.nest_x, cfg.nest_y = 0.64, 0.64
+    rng = np.random.default_rng(17)
+    f0 = rng.random((1, 128, 128), dtype=np.float32)
+    n = 30000
+    x, y, th, _ = rand_agents(rng, cfg, n)
+    st = rng.integers(0, 4, n)  # includes EMPTY and IDLE
+    # homing agents around the nest at every distance band (STOP ring, inside radius, far)
+    x[:3000] = (0.64 + rng.uniform(-0.08, 0.08, 3000)).astype(np.float32)
+    y[:3000] = (0.64 + rng.uniform(-0.08, 0.08, 3000)).astype(np.float32)
+    st[:3000] = abi.STATE_HOMING
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    o.set_field(f0)
+    g = PheroField(cfg)
+    g.upload(f0)
+    sw = Swarm(x, y, th, st)
+    dec_g = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for it in range(5):
+        dec_o = o.agents_step(a_np)
+        g.agents_step(sw, decisions=dec_g)
+        assert (dec_g.cpu().numpy() == dec_o).all(), f"decisions differ at iteration {it}"
+        _compare_agents(sw, a_np, f"iteration {it}")
+    hist = np.bincount(dec_o, minlength=6)
+    assert hist[abi.DEC_STOP] > 0 and hist[abi.DEC_KEEP] > 0 and hist[abi.DEC_LEFT] > 0
+    c = g.counters()
+    assert list(c.decisions) == [int(v) for v in o.counters[:6]]
+    g.close()
+
+
+# ----------------------------------------------------------------------------- whole tick
+def _run_ticks(cfg, n_agents, nticks, seed, check_every, start_delay=0.0, states=None, margin=0.05):
+    rng = np.random.default_rng(seed)
+    x, y, th, st = rand_agents(rng, cfg, n_agents, margin=margin, states=states)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    o.start_delay = start_delay
+    g = PheroField(cfg)
+    g.set_time(0.0, start_delay)
+    sw = Swarm(x, y, th, st)
+    done = 0
+    while done < nticks:
+        k = min(check_every, nticks - done)
+        o.tick(a_np, k)
+        g.step(sw, k)
+        done += k
+        _compare_agents(sw, a_np, f"tick {done}")
+        r_o, q_o, _ = dense.cells_of(cfg, a_np.x, a_np.y)
+        got = sw.to_numpy()
+        r_g, q_g, _ = dense.cells_of(cfg, got["x"], got["y"])
+        assert (r_o == r_g).all() and (q_o == q_g).all(), "agent cell indices differ"
+        assert_bitexact(g.snapshot(), o.field, f"field at tick {done}")
+    c = g.counters()
+    assert c.deposits == int(o.counters[8]), "deposit totals differ"
+    assert list(c.decisions) == [int(v) for v in o.counters[:6]], "decision histogram differs"
+    assert c.ticks == nticks
+    return o, g, a_np, sw
+
+
+def test_tick_config1_first_100_steps_bitexact():
+    # BASELINE config 1: 1024 x 1024 single channel, 4096 agents, evaporate+diffuse+deposit
+    cfg = make_cfg(1024, 1024, 1, 5, D=0.1)
+    cfg.evap_keep[0] = 0.9
+    o, g, a_np, sw = _run_ticks(cfg, 4096, 100, seed=1234, check_every=10)
+    assert o.counters[abi.DEC_LEFT] + o.counters[abi.DEC_RIGHT] > 0
+    g.close()
+
+
+def test_tick_field_after_1000_steps_within_tolerance():
+    cfg = make_cfg(256, 256, 1, 9, D=0.1)
+    cfg.evap_keep[0] = 0.98
+    o, g, a_np, sw = _run_ticks(cfg, 2048, 1000, seed=99, check_every=250)
+    got, want = g.snapshot(), o.field
+    tol = 1e-5 * float(want.max())  # north_star: within 1e-5 of the maximum level
+    assert np.abs(got - want).max() <= tol
+    g.close()
+
+
+def test_tick_two_channel_fsm_foraging():
+    # config-4-like: two trails, nest + 8 food sources on a ring, FSM on
+    cfg = make_cfg(256, 256, 2, 5, D=0.05)
+    cfg.fsm = 1
+    cfg.nest_x, cfg.nest_y = 1.28, 1.28
+    cfg.n_food = 8
+    for k in range(8):
+        cfg.food_x[k] = 1.28 + 0.35 * 2.56 * np.cos(2 * np.pi * k / 8)
+        cfg.food_y[k] = 1.28 + 0.35 * 2.56 * np.sin(2 * np.pi * k / 8)
+    cfg.food_radius = 0.1
+    rng = np.random.default_rng(5)
+    n = 4000
+    x = (1.28 + rng.uniform(-0.9, 0.9, n)).astype(np.float32)
+    y = (1.28 + rng.uniform(-0.9, 0.9, n)).astype(np.float32)
+    th = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    st = rng.integers(1, 3, n)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    sw = Swarm(x, y, th, st)
+    for _ in range(6):
+        o.tick(a_np, 50)
+        g.step(sw, 50)
+        _compare_agents(sw, a_np)
+        assert_bitexact(g.snapshot(), o.field)
+    c = g.counters()
+    assert c.food_grabbed == int(o.counters[6]) and c.food_delivered == int(o.counters[7])
+    assert c.food_grabbed > 0 and c.food_delivered > 0
+    g.close()
+
+
+def test_tick_start_delay_random_walk():
+    # before t = 5 s no deposit and no sensing (sup:731-744); 100 ticks cross the 5 s mark at 79
+    cfg = make_cfg(128, 256, 1, 5)
+    o, g, a_np, sw = _run_ticks(cfg, 1000, 100, seed=4, check_every=20, start_delay=5.0)
+    assert int(o.counters[abi.DEC_NONE]) == 1000 * 79
+    g.close()
+
+
+# ----------------------------------------------------------------------------- migration
+def test_migrate_pack_unpack_roundtrip():
+    H, W = 64, 64
+    cfg = make_cfg(H, W, 1, 5)
+    top = cfg.copy(); top.row0, top.row1 = 0, 32
+    bot = cfg.copy(); bot.row0, bot.row1 = 32, 64
+    gt, gb = PheroField(top), PheroField(bot)
+    rng = np.random.default_rng(2)
+    n, cap_slots, cap = 1000, 1500, 256
+    x, y, th, st = rand_agents(rng, cfg, n)
+    x[:] = rng.uniform(0.25, 0.3199, n)  # all in the top strip, near the boundary (row 32 = 0.32)
+    x[:100] = rng.uniform(0.32, 0.33, 100)  # these have crossed
+    st_arr = np.ones(n, np.int64)
+    sw_t = Swarm(x, y, th, st_arr, capacity=cap_slots)
+    sw_b = Swarm(np.zeros(0), np.zeros(0), np.zeros(0), capacity=cap_slots)
+    words = abi.PF_MIGRATE_WORDS * (cap + 1)
+    up = torch.zeros(words, dtype=torch.int32, device="cuda")
+    down = torch.zeros(words, dtype=torch.int32, device="cuda")
+    gt.migrate_pack(sw_t, up, down, cap)
+    assert int(up[0]) == 0 and int(down[0]) == 100
+    gb.migrate_unpack(sw_b, down, cap)
+    a_t, a_b = sw_t.to_numpy(), sw_b.to_numpy()
+    alive_t = (a_t["meta"] & 3) != 0
+    alive_b = (a_b["meta"] & 3) != 0
+    assert alive_t.sum() == 900 and alive_b.sum() == 100
+    assert sorted(a_b["gid"][alive_b].tolist()) == list(range(100))
+    # deterministic placement: k-th record -> k-th empty slot, records ordered by source slot
+    assert a_b["gid"][:100].tolist() == list(range(100))
+    assert_bitexact(a_b["x"][:100], x[:100])
+    c = gt.counters()
+    assert c.migrated_out == 100 and gb.counters().migrated_in == 100
+    gt.close(); gb.close()
+
+
+def test_evaporate_trail_known_answers(golden_dir):
+    # sup:519-525 compounded once per tick while 2 <= age <= 4 reproduces pheromonelevels.txt
+    import json
+    lv = json.load(open(golden_dir / "pheromonelevels.json"))["e2"]
+    cfg = make_cfg(32, 32, 1, 0)
+    g = PheroField(cfg)
+    ages = torch.tensor([2.048 + 0.064 * k for k in range(14)], dtype=torch.float64, device="cuda")
+    inten = torch.tensor([20.0], dtype=torch.float64, device="cuda")
+    vals = []
+    for k in range(14):
+        inten = g.evaporate_trail(ages[k:k + 1], inten)
+        vals.append(float(inten))
+    for want, nticks in zip(lv[:4], (14, 13, 12, 11)):
+        assert abs(vals[nticks - 1] - want) < 1e-12
+    g.close()
