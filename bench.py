@@ -1,0 +1,520 @@
+#!/usr/bin/env python
+"""bench.py — whole-tick throughput of the pheromone hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                     (CPU arm: the oracle port on host cores)
+
+One "step" = one supervisor tick over the whole arena and every agent, in the reference order
+deposit -> sense/decide -> evaporate+diffuse -> move. Workload (BASELINE.json configs[3], the one
+the metric and the north_star target are quoted on; it fits one GPU): 32768 x 32768 cells, two
+channels, 2^24 agents, uniform, fp32. At N > 1 the same global arena is split into row strips
+(strong scaling), one halo row per channel per internal boundary per tick plus agent migration.
+
+Prints ONE JSON line. `value` = grid cell-updates/s with everything resident in HBM (agent-steps/s
+is reported next to it); `e2e` = the same tick driven through the reference-facing call with the
+poses coming from pinned HOST memory and the wheel speeds/decisions going back to the host every
+step; `roofline` = the evaporate+diffuse kernel's algorithmic bytes over its device time (CUDA
+events recorded on the launching stream inside the timed region) against the measured HBM copy
+rate; `cpu_baseline` = the C oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from swarm_robotics_pheromones_b200 import abi  # noqa: E402
+
+CONFIGS = {
+    # name: (H, W, C, agents, stencil)
+    "c1": (1024, 1024, 1, 4096, 5),
+    "c2": (8192, 8192, 1, 1 << 20, 9),
+    "c3": (32768, 32768, 2, 1 << 24, 9),
+    "c4": (16384, 16384, 2, 1 << 22, 9),
+}
+BYTES_PER_CELL_UPDATE = 8          # SURVEY §8d / BASELINE.md §5
+BYTES_PER_AGENT_STEP = 56
+BYTES_PER_DEPOSIT = 12 + 8
+
+
+def make_config(name: str, H=None, W=None, C=None, agents=None, stencil=None):
+    h, w, c, n, st = CONFIGS[name]
+    H, W, C, n, st = H or h, W or w, C or c, agents or n, stencil if stencil is not None else st
+    cfg = abi.default_config(H, W, C)
+    cfg.stencil = st
+    for k in range(C):
+        cfg.evap_keep[k] = 1.0 - 0.1
+        cfg.diffusion[k] = 0.1
+    if name == "c4":  # nest disc + 8 food sources on a ring at 0.35 W
+        cfg.fsm = 1
+        cx, cy = 0.5 * H * cfg.cell_size, 0.5 * W * cfg.cell_size
+        cfg.nest_x, cfg.nest_y = cx, cy
+        cfg.n_food = 8
+        for k in range(8):
+            cfg.food_x[k] = cx + 0.35 * W * cfg.cell_size * np.cos(2 * np.pi * k / 8)
+            cfg.food_y[k] = cy + 0.35 * W * cfg.cell_size * np.sin(2 * np.pi * k / 8)
+        cfg.food_radius = 0.16
+    return cfg, n
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def stencil_traffic_from_profile():
+    """dram bytes per launch of the stencil kernel from the committed ncu summary, if any"""
+    p = ROOT / "profiles" / "stencil_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_throughput(cfg_full, n_agents_full, budget_s=12.0, threads=None, stencil=None):
+    """Time the C oracle on host cores on a bounded sample: each thread owns an independent arena of
+    `rows_s` x W x C cells with the same agent density, and runs whole ticks."""
+    from oracle import dense
+    dense.lib()
+    T = threads or max(1, min(os.cpu_count() or 1, 64))
+    W = cfg_full.W
+    rows_s = max(64, min(cfg_full.H, (1 << 24) // max(1, W * cfg_full.C)))  # ~16 M cells/thread
+    n_s = max(1, int(n_agents_full * (rows_s / cfg_full.H)))
+    cfg = abi.default_config(rows_s, W, cfg_full.C)
+    cfg.stencil = cfg_full.stencil
+    for k in range(cfg_full.C):
+        cfg.evap_keep[k] = cfg_full.evap_keep[k]
+        cfg.diffusion[k] = cfg_full.diffusion[k]
+    results = [0] * T
+    worlds = []
+    for t in range(T):
+        rng = np.random.default_rng(1234 + t)
+        a = dense.AgentsNP(rng.uniform(0, rows_s * cfg.cell_size, n_s),
+                           rng.uniform(0, W * cfg.cell_size, n_s), rng.uniform(-np.pi, np.pi, n_s))
+        worlds.append((dense.DenseOracle(cfg), a))
+    worlds[0][0].tick(worlds[0][1], 1)  # warm-up / page-in
+    stop_at = time.perf_counter() + budget_s
+
+    def work(t):
+        o, a = worlds[t]
+        k = 0
+        while True:
+            o.tick(a, 1)  # ctypes releases the GIL
+            k += 1
+            if time.perf_counter() >= stop_at:
+                break
+        results[t] = k
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    ticks = sum(results)
+    cells = ticks * rows_s * W * cfg.C
+    return {
+        "value": cells / dt, "unit": "cell-updates/s", "agent_steps_per_s": ticks * n_s / dt,
+        "cores": T, "kind": "port",
+        "sample": f"{T} threads x independent {rows_s}x{W}x{cfg.C} arenas with {n_s} agents each "
+                  f"(same density and stencil as the workload), {ticks} whole ticks in {dt:.1f} s, "
+                  f"oracle/pf_oracle.c (gcc -O2, scalar)",
+    }, dt / max(1, ticks) * T
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
+    budget = max(5.0, min(60.0, 4.0 * (args.steps + args.warmup)))
+    cb, ms = cpu_port_throughput(cfg, n, budget_s=budget)
+    line = {
+        "impl": "reference", "metric": "grid cell-updates/s (agent-steps/s alongside)",
+        "value": cb["value"], "unit": "cell-updates/s", "agent_steps_per_s": cb["agent_steps_per_s"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_dict(args, cfg, n),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_dict(args, cfg, n):
+    return {"workload": f"{args.config}: {cfg.H}x{cfg.W} cells x {cfg.C} channel(s), {n} agents, "
+                        f"{cfg.stencil}-point evaporate+diffuse, deposit, sense/decide/move",
+            "grid": [cfg.H, cfg.W], "channels": cfg.C, "agents": n, "stencil": cfg.stencil,
+            "parallelism": f"row strips x{args.gpus}" if args.gpus > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (field >> 126 MB)" if cfg.H * cfg.W * cfg.C * 4 > (1 << 28)
+            else "field fits L2: L2 flushed between timed steps is NOT applied; reported as L2-resident"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def init_agents_torch(cfg, n, device, seed=1234):
+    import torch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    xmax, ymax = cfg.H * cfg.cell_size, cfg.W * cfg.cell_size
+    x = torch.rand(n, generator=g) * xmax
+    y = torch.rand(n, generator=g) * ymax
+    th = (torch.rand(n, generator=g) * 2 - 1) * float(np.pi)
+    if cfg.fsm:  # c4: start around the nest, +-5 % of the arena width
+        x = cfg.nest_x + (torch.rand(n, generator=g) * 2 - 1) * 0.05 * xmax
+        y = cfg.nest_y + (torch.rand(n, generator=g) * 2 - 1) * 0.05 * ymax
+    return x.float().numpy(), y.float().numpy(), th.float().numpy()
+
+
+def run_single(args):
+    import torch
+
+    from swarm_robotics_pheromones_b200.compat import ReferenceCompat
+    from swarm_robotics_pheromones_b200.field import PheroField, Swarm
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(0)
+    cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
+    x, y, th = init_agents_torch(cfg, n, "cuda")
+    field = PheroField(cfg)
+    field.set_stencil_variant(args.variant, args.rows_per_cta)
+    swarm = Swarm(x, y, th)
+    field.reserve_agents(n)
+    field.set_time(0.0, 0.0)
+    cells = cfg.H * cfg.W * cfg.C
+
+    def run_ticks(k):
+        """k whole ticks; every --sort-every ticks the agent arrays are re-ordered by cell (inside
+        the timed region: it is part of the cost of keeping the gathers local)"""
+        done = 0
+        while done < k:
+            if args.sort_every > 0 and state["since_sort"] >= args.sort_every:
+                field.sort_agents(swarm)
+                state["since_sort"] = 0
+                state["sorts"] += 1
+            m = k - done
+            if args.sort_every > 0:
+                m = min(m, args.sort_every - state["since_sort"])
+            field.step(swarm, m)
+            done += m
+            state["since_sort"] += m
+
+    state = {"since_sort": args.sort_every, "sorts": 0}  # first call sorts the initial population
+
+    # ---- device-resident throughput
+    run_ticks(args.warmup)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    l0 = field.launch_count()
+    field.profile(True)
+    field.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    torch.cuda.synchronize()
+    sorts0 = state["sorts"]
+    state["since_sort"] = args.sort_every  # the timed region pays ceil(K / sort_every) sorts
+    e0.record()
+    run_ticks(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    sorts_timed = state["sorts"] - sorts0
+    prof = field.profile_read(reset=True)
+    field.profile(False)
+    launches = field.launch_count() - l0
+    ms_per_step = ms / args.steps
+    value = cells * args.steps / (ms * 1e-3)
+    agent_rate = n * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (evaporate+diffuse), live device time per launch
+    peak, peak_src = measured_peaks()
+    st_ms = prof.stencil_ms / max(1, prof.ticks)
+    ach = cells * BYTES_PER_CELL_UPDATE / (st_ms * 1e-3) / 1e9
+    tr = stencil_traffic_from_profile()
+    roofline = {"bound": "hbm", "kernel": "evaporate+diffuse stencil", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                "frac_of_8TBs_nominal": ach / 8000.0,
+                "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL_UPDATE,
+                "launch_ms": st_ms,
+                "phase_ms": {"deposit": prof.deposit_ms / max(1, prof.ticks), "stencil": st_ms,
+                             "agents(side stream, overlapped)": prof.agents_ms / max(1, prof.ticks)},
+                "whole_tick": {"algorithmic_bytes": cells * 8 + n * (BYTES_PER_AGENT_STEP + 12) + 8 * min(n, cells),
+                               "achieved_GBs": (cells * 8 + n * (BYTES_PER_AGENT_STEP + 12) + 8 * min(n, cells))
+                               / (ms_per_step * 1e-3) / 1e9}}
+    roofline["whole_tick"]["frac"] = roofline["whole_tick"]["achieved_GBs"] / peak
+
+    # ---- end to end through the reference-facing call, host poses in / wheel speeds out
+    rc = ReferenceCompat.from_field(field, swarm)
+    pose = rc._h_pose
+    cur = swarm.to_numpy()
+    pose[0].copy_(torch.from_numpy(cur["x"]))
+    pose[1].copy_(torch.from_numpy(cur["y"]))
+    pose[2].copy_(torch.from_numpy(cur["theta"]))
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        rc.tick_host(pose)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        wl, wr, dec = rc.tick_host(pose)  # synchronous: the supervisor needs the speeds
+        pose[0].add_(1e-3)  # the "physics" moves the robots between ticks (host side)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": cells * e2e_steps / e2e_s, "unit": "cell-updates/s",
+           "agent_steps_per_s": n * e2e_steps / e2e_s, "ms_per_step": e2e_s / e2e_steps * 1e3,
+           "steps": e2e_steps, "h2d_bytes_per_step": rc.h2d_bytes, "d2h_bytes_per_step": rc.d2h_bytes,
+           "call": "ReferenceCompat.tick_host(pinned poses [3][N]) -> (wl, wr, decision) on host"}
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle port on this box's host cores
+    cb = None
+    if not args.no_cpu:
+        cb, _ = cpu_port_throughput(cfg, n, budget_s=args.cpu_seconds)
+
+    line = {
+        "metric": "grid cell-updates/s (agent-steps/s alongside)", "value": value,
+        "unit": "cell-updates/s", "agent_steps_per_s": agent_rate, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_dict(args, cfg, n), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+        "stencil_variant": args.variant, "agent_sort_every": args.sort_every,
+        "agent_sorts_in_timed_region": sorts_timed,
+    }
+    print(json.dumps(line), flush=True)
+    field.close()
+
+
+def run_sharded(args):
+    import torch
+    import torch.distributed as dist
+
+    from swarm_robotics_pheromones_b200 import sharded
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
+    scfg = sharded.strip_config(cfg, world, rank, device=local)
+    # every rank draws the same global population and keeps its own strip's agents
+    x, y, th = init_agents_torch(cfg, n, "cuda")
+    rows = sharded.agent_rows(cfg, x)
+    mine = np.nonzero((rows >= scfg.row0) & (rows < scfg.row1))[0]
+    n_local = len(mine)
+    cap = int(n_local * 1.25) + 4096
+    mcap = max(4096, int(4 * n / cfg.H) + 4096)
+    strip = sharded.CudaStrip(scfg, x[mine], y[mine], th[mine], np.full(n_local, abi.STATE_SEARCHING),
+                              mine.astype(np.uint32), cap, mcap)
+    del x, y, th, rows
+    strip.field.set_stencil_variant(args.variant, args.rows_per_cta)
+    worker = sharded.StripWorker(strip, rank, world)
+    drv = sharded.DistDriver(worker, overlap=not args.no_overlap)
+    cells = cfg.H * cfg.W * cfg.C
+
+    for _ in range(args.warmup):
+        drv.tick(True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    l0 = strip.field.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        drv.tick(True)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = strip.field.launch_count() - l0
+
+    # stencil-only time of this strip (roofline per GPU), same event method
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    torch.cuda.synchronize()
+    s0.record()
+    for _ in range(reps):
+        strip.field.step_field_rows(0, strip.rows)
+    s1.record()
+    torch.cuda.synchronize()
+    st_ms = s0.elapsed_time(s1) / reps
+    peak, peak_src = measured_peaks()
+    local_cells = strip.rows * cfg.W * cfg.C
+    ach = local_cells * BYTES_PER_CELL_UPDATE / (st_ms * 1e-3) / 1e9
+
+    # e2e: per-rank host poses in, wheel speeds out, no motion on the device
+    sw = strip.swarm
+    nl = sw.n
+    h_pose = torch.empty((3, nl), dtype=torch.float32).pin_memory()
+    d_pose = torch.empty((3, nl), dtype=torch.float32, device="cuda")
+    h_out = torch.empty((2, nl), dtype=torch.float32).pin_memory()
+    d_out = torch.empty((2, nl), dtype=torch.float32, device="cuda")
+    h_dec = torch.empty(nl, dtype=torch.int32).pin_memory()
+    h_pose[0].copy_(sw.x.cpu()); h_pose[1].copy_(sw.y.cpu()); h_pose[2].copy_(sw.theta.cpu())
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_tick():
+        d_pose.copy_(h_pose, non_blocking=True)
+        strip.field.observe(sw, d_pose[0], d_pose[1], d_pose[2])
+        drv.tick(True, move=False)
+        d_out[0].copy_(sw.wl); d_out[1].copy_(sw.wr)
+        h_out.copy_(d_out, non_blocking=True)
+        h_dec.copy_((sw.meta & abi.META_DEC_MASK) >> abi.META_DEC_SHIFT, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_tick()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_tick()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    bytes_io = torch.tensor([h_pose.numel() * 4, h_out.numel() * 4 + h_dec.numel() * 4], device="cuda",
+                            dtype=torch.float64)
+    dist.all_reduce(bytes_io)
+    counts = torch.tensor([float(sw.alive().sum().item())], device="cuda", dtype=torch.float64)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts)
+
+    if rank == 0:
+        line = {
+            "metric": "grid cell-updates/s (agent-steps/s alongside)",
+            "value": cells * args.steps / (ms * 1e-3), "unit": "cell-updates/s",
+            "agent_steps_per_s": n * args.steps / (ms * 1e-3), "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_dict(args, cfg, n), "clocks": clocks,
+            "e2e": {"value": cells * e2e_steps / e2e_s, "unit": "cell-updates/s",
+                    "agent_steps_per_s": n * e2e_steps / e2e_s, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "steps": e2e_steps, "h2d_bytes_per_step": int(bytes_io[0].item()),
+                    "d2h_bytes_per_step": int(bytes_io[1].item()),
+                    "call": "per rank: pinned poses -> pf_agents_observe -> sharded tick -> speeds to host"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "evaporate+diffuse stencil (rank 0 strip, timed alone)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "peak_source": peak_src, "traffic": None, "launch_ms": st_ms,
+                         "algorithmic_bytes_per_launch": local_cells * BYTES_PER_CELL_UPDATE},
+            "cpu_baseline": None,
+            "agents_per_rank": [int(c.item()) for c in allc],
+            "halo_overlap": not args.no_overlap, "stencil_variant": args.variant,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    strip.field.close()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--grid", type=int, default=None, help="override H = W (debug)")
+    ap.add_argument("--channels", type=int, default=None)
+    ap.add_argument("--agents", type=int, default=None)
+    ap.add_argument("--stencil", type=int, default=None, choices=[0, 5, 9])
+    ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant (0 auto)")
+    ap.add_argument("--rows-per-cta", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--sort-every", type=int, default=32,
+                    help="re-order the agent arrays by cell every this many ticks (0 = never)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        args.gpus = world
+        run_sharded(args)
+    else:
+        run_single(args)
+
+
+if __name__ == "__main__":
+    main()

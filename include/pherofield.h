@@ -74,6 +74,7 @@ extern "C" {
 #define PF_META_DEC_SHIFT 3            /* bits 3-5: last PF_DEC_*                               */
 #define PF_META_DEC_MASK 0x38u
 #define PF_META_CARRY 0x40u            /* bit 6: carrying food (fsm mode)                       */
+#define PF_META_HASPOS 0x80u           /* bit 7: a previous observed position exists (sup:281)  */
 #define PF_META_COUNT_SHIFT 8          /* bits 8-31: deposits made so far (len(global grid))    */
 
 /* step flags */
@@ -248,6 +249,21 @@ int pf_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* de
  * Not valid on a sharded handle (the host drives the exchange between the phases).
  * Replaces Controller.startPheromone / Controller.homing (sup:565-607, 627-663). */
 int pf_step(pf_handle* h, const pf_agents* a, int nsteps, void* stream);
+/* pf_step with a phase mask (PF_STEP_*): e.g. without PF_STEP_MOVE when the caller (Webots in the
+ * reference) owns the positions and feeds them through pf_agents_observe every tick. */
+int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t flags, void* stream);
+/* Take externally measured poses (supervisor.getSelf().getPosition(), sup:255-258): shifts
+ * current -> previous and sets the moved flag = sqrt(dx^2+dy^2) >= move_threshold, True on the
+ * first observation. theta_new may be NULL (heading kept).
+ * Replaces storingPosition + has_moved (sup:279-289, 260-273). */
+int pf_agents_observe(pf_handle* h, const pf_agents* a, const float* x_new, const float* y_new,
+                      const float* theta_new, void* stream);
+/* Physically re-order the agent arrays (all seven, in place) by cell, row-major, empty slots last.
+ * Agents move well under one cell per tick, so calling this every few dozen ticks keeps the sense
+ * gathers and the deposit scatter local in HBM. Identity is carried by gid. Results of every other
+ * call are independent of the order (per-cell deposit sums are order-independent for the
+ * reference's exactly representable amounts 1, 5, 20). No reference counterpart. */
+int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream);
 int pf_set_time(pf_handle* h, double time_s, double start_delay_s);
 int pf_get_time(const pf_handle* h, double* time_s, uint64_t* ticks);
 
@@ -274,6 +290,17 @@ int pf_counters_reset(pf_handle* h, void* stream);
 
 /* number of kernels this handle has launched (bench.py reports it as gpu_launches) */
 int pf_launch_count(const pf_handle* h, uint64_t* n);
+
+/* Per-phase device times of pf_step, from CUDA events recorded on the launching streams while
+ * profiling is enabled (bench.py's live roofline numbers). Times are sums over `ticks` ticks. */
+typedef struct pf_profile {
+  uint64_t ticks;
+  double deposit_ms;  /* key build + radix sort + segmented sum */
+  double stencil_ms;  /* evaporate + diffuse kernel (runs concurrently with the agent kernel) */
+  double agents_ms;   /* sense/decide/move kernel, on the side stream */
+} pf_profile;
+int pf_profile_enable(pf_handle* h, int on);
+int pf_profile_read(pf_handle* h, pf_profile* out_host, int reset);
 
 /* which stencil kernel variant pf_step_field uses: 0 = auto, 1 = register sliding window (LDG),
  * 2 = TMA + mbarrier pipelined shared-memory tiles. For tuning sweeps. */

@@ -37,6 +37,9 @@ SIGNATURES = {
     "pf_sense": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pf_agents_step": (C.c_int, [_vp, _agp, C.c_uint32, _vp, _vp]),
     "pf_step": (C.c_int, [_vp, _agp, C.c_int, _vp]),
+    "pf_step_ex": (C.c_int, [_vp, _agp, C.c_int, C.c_uint32, _vp]),
+    "pf_agents_observe": (C.c_int, [_vp, _agp, _vp, _vp, _vp, _vp]),
+    "pf_agents_sort": (C.c_int, [_vp, _agp, _vp]),
     "pf_set_time": (C.c_int, [_vp, C.c_double, C.c_double]),
     "pf_get_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pf_evaporate_trail": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_double, _vp, _vp]),
@@ -45,6 +48,8 @@ SIGNATURES = {
     "pf_counters_host": (C.c_int, [_vp, C.POINTER(abi.PFCounters), _vp]),
     "pf_counters_reset": (C.c_int, [_vp, _vp]),
     "pf_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "pf_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "pf_profile_read": (C.c_int, [_vp, C.POINTER(abi.PFProfile), C.c_int]),
     "pf_set_stencil_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
 }
 

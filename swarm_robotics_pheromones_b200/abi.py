@@ -27,6 +27,7 @@ META_MOVED = 0x4
 META_DEC_SHIFT = 3
 META_DEC_MASK = 0x38
 META_CARRY = 0x40
+META_HASPOS = 0x80
 META_COUNT_SHIFT = 8
 
 STEP_DEPOSIT, STEP_SENSE, STEP_FIELD, STEP_MOVE, STEP_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
@@ -125,6 +126,11 @@ class PFCounters(C.Structure):
         ("migrated_in", C.c_uint64),
         ("migrate_dropped", C.c_uint64),
     ]
+
+
+class PFProfile(C.Structure):
+    _fields_ = [("ticks", C.c_uint64), ("deposit_ms", C.c_double), ("stencil_ms", C.c_double),
+                ("agents_ms", C.c_double)]
 
 
 def default_config(H: int, W: int, C_: int = 1, *, cell_size: float = 0.01, device: int = 0,

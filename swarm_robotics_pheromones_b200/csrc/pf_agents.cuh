@@ -349,6 +349,29 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
     atomicAdd(&counters[2 + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 
+// storingPosition + has_moved (reference sup:279-289, 260-273) for externally measured poses
+__global__ void __launch_bounds__(256)
+k_agents_observe(PFDev p, long long n, float* __restrict__ ax, float* __restrict__ ay,
+                 float* __restrict__ ath, uint32_t* __restrict__ ameta,
+                 const float* __restrict__ nx, const float* __restrict__ ny,
+                 const float* __restrict__ nth) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t mt = ameta[i];
+  if ((mt & PF_META_STATE_MASK) == PF_STATE_EMPTY) return;
+  float x = nx[i], y = ny[i];
+  uint32_t moved = PF_META_MOVED;  // old_pos is None -> True (sup:261-262)
+  if (mt & PF_META_HASPOS) {
+    float dx = fsub(x, ax[i]), dy = fsub(y, ay[i]);
+    float dist = fsqrt(fadd(fmul(dx, dx), fmul(dy, dy)));
+    moved = (dist >= p.move_thr) ? PF_META_MOVED : 0u;
+  }
+  ax[i] = x;
+  ay[i] = y;
+  if (nth) ath[i] = nth[i];
+  ameta[i] = (mt & ~PF_META_MOVED) | moved | PF_META_HASPOS;
+}
+
 // ------------------------------------------------------------------------------------------
 // migration between row strips
 // ------------------------------------------------------------------------------------------
@@ -469,3 +492,30 @@ __global__ void k_evaporate_trail(long long n, const double* __restrict__ elapse
 }
 
 __global__ void k_tick_counter(unsigned long long* counters) { counters[0] += 1ull; }
+
+// ------------------------------------------------------------------------------------------
+// spatial re-ordering of the agent arrays (locality for the sense gathers and the deposit scatter)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sort_keys(PFDev p, long long n, const float* __restrict__ x, const float* __restrict__ y,
+            const uint32_t* __restrict__ meta, uint32_t* __restrict__ keys,
+            uint32_t* __restrict__ idx, uint32_t sentinel) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t key = sentinel;  // empty slots go to the end
+  if ((meta[i] & PF_META_STATE_MASK) != PF_STATE_EMPTY) {
+    int r, q;
+    pf_cell(p, x[i], y[i], r, q);
+    key = (uint32_t)((long long)r * p.W + q);
+  }
+  keys[i] = key;
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+k_permute_u32(long long n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ src,
+              uint32_t* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = src[perm[i]];
+}

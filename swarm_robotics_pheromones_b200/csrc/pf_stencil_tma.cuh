@@ -17,7 +17,7 @@ constexpr int kTmaRowFloats = kTmaCols + 8;   // + 4 halo floats each side
 constexpr int kTmaThreads = kTmaWarps * 32 + 32;  // + producer warp
 
 struct TmaStencilState {
-  bool attr_set[3][2];
+  bool attr_set[3][4];
   char err[256];
 };
 
@@ -186,16 +186,29 @@ static int tma_launch_one(TmaStencilState* st, int slot, const StencilArgs& a, d
 
 // rows_per_cta <= 0 selects the default. Returns PF_ESTATE when the shape is not supported
 // (the caller then uses the register sliding-window kernel).
-static int tma_stencil_launch(TmaStencilState* st, const pf_config& cfg, const PFDev& d, StencilArgs a,
+static int tma_stencil_launch(TmaStencilState* st, int shape, const pf_config& cfg, const PFDev& d, StencilArgs a,
                               int rows_per_cta, cudaStream_t s) {
   (void)cfg;
   if (d.W % 4 != 0 || d.W < 128) return PF_ESTATE;
   const int nrows = a.r_end - a.r_begin;
-  int rpc = rows_per_cta > 0 ? rows_per_cta : 128;
+  int rpc = rows_per_cta > 0 ? rows_per_cta : (d.stencil == 9 ? 64 : 128);
+  {  // small fields: keep at least ~2 CTAs per SM in flight
+    const long long xb = (d.W + kTmaCols - 1) / kTmaCols;
+    while (rpc > 8 && xb * d.C * ((nrows + rpc - 1) / rpc) < 296) rpc /= 2;
+  }
   if (rpc > nrows) rpc = nrows;
   a.rows_per_cta = rpc;
   dim3 grid((d.W + kTmaCols - 1) / kTmaCols, (nrows + rpc - 1) / rpc, d.C);
-  if (d.stencil == 0) return tma_launch_one<0, 4, 4>(st, 0, a, grid, s);
-  if (d.stencil == 5) return tma_launch_one<5, 4, 4>(st, 0, a, grid, s);
-  return tma_launch_one<9, 4, 4>(st, 0, a, grid, s);
+#define PF_TMA_DISPATCH(R, S, SLOT)                                             \
+  do {                                                                          \
+    if (d.stencil == 0) return tma_launch_one<0, R, S>(st, SLOT, a, grid, s);   \
+    if (d.stencil == 5) return tma_launch_one<5, R, S>(st, SLOT, a, grid, s);   \
+    return tma_launch_one<9, R, S>(st, SLOT, a, grid, s);                       \
+  } while (0)
+  // ring shapes: rows per stage x stages (x 4128 B per row)
+  if (shape == 1) PF_TMA_DISPATCH(8, 3, 1);   //  99 KB: 2 CTAs/SM
+  if (shape == 2) PF_TMA_DISPATCH(2, 8, 2);   //  66 KB: 3 CTAs/SM, finer stages
+  if (shape == 3) PF_TMA_DISPATCH(4, 6, 3);   //  99 KB: 2 CTAs/SM, deeper
+  PF_TMA_DISPATCH(4, 4, 0);                   //  66 KB: 3 CTAs/SM
+#undef PF_TMA_DISPATCH
 }

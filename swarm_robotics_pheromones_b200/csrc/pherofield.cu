@@ -43,8 +43,16 @@ struct pf_handle {
   uint64_t ticks;
   int variant, rows_per_cta;
   TmaStencilState tma;
+  // profiling: ring of per-tick events
+  int prof_on;
+  int prof_used;
+  cudaEvent_t* prof_ev;  // kProfSlots x 5: main t0,t1,t2 ; side a0,a1
+  unsigned char prof_has_agents[256];
+  pf_profile prof;
   char err[512];
 };
+
+constexpr int kProfSlots = 256;
 
 static int set_err(pf_handle* h, int code, const char* fmt, ...) {
   char* dst = h ? h->err : g_create_err;
@@ -259,6 +267,10 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->prof_ev) {
+    for (int i = 0; i < kProfSlots * 5; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+  }
   delete h;
   return PF_OK;
 }
@@ -280,7 +292,7 @@ extern "C" int pf_reserve_agents(pf_handle* h, int64_t max_agents) {
   if (h->cub_temp) cudaFree(h->cub_temp);
   h->scratch = nullptr; h->cub_temp = nullptr; h->cap = 0;
   long long cap = (max_agents + 1023) / 1024 * 1024;
-  PF_CUDA(h, cudaMalloc(&h->scratch, (size_t)cap * 16));
+  PF_CUDA(h, cudaMalloc(&h->scratch, (size_t)cap * 20));  // + 4 B/agent for the permute pass
   size_t sort_bytes = 0, scan_bytes = 0;
   PF_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                              (const float*)nullptr, (float*)nullptr, (int)cap, 0, 32, (cudaStream_t)0));
@@ -403,9 +415,12 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) 
     return PF_OK;
   }
   int variant = h->variant;
-  if (variant == 0) variant = 1;
-  if (variant == 2) {
-    int rc = tma_stencil_launch(&h->tma, h->cfg, d, a, h->rows_per_cta, s);
+  // auto: measured on B200 at 32768^2 x 2 (profiles/r01_k1_sweep.md): the TMA ring reaches 6535 GB/s
+  // (5-point) / 6345 GB/s (9-point) against 5236 / 5055 for the register window; pure evaporation
+  // (no neighbours) is a plain stream and the register window wins (6814 GB/s).
+  if (variant == 0) variant = (d.stencil != 0 && d.W >= 512) ? 2 : 1;
+  if (variant >= 2) {
+    int rc = tma_stencil_launch(&h->tma, variant - 2, h->cfg, d, a, h->rows_per_cta, s);
     if (rc == PF_OK) { h->launches++; return PF_OK; }
     if (rc != PF_ESTATE) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
     // PF_ESTATE: shape not supported by the TMA variant -> register sliding window
@@ -458,7 +473,7 @@ extern "C" int pf_swap(pf_handle* h) {
 }
 
 extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_cta) {
-  if (!h || variant < 0 || variant > 2 || rows_per_cta < 0) return PF_EINVAL;
+  if (!h || variant < 0 || variant > 5 || rows_per_cta < 0) return PF_EINVAL;
   h->variant = variant;
   h->rows_per_cta = rows_per_cta;
   return PF_OK;
@@ -568,7 +583,70 @@ extern "C" int pf_get_time(const pf_handle* h, double* time_s, uint64_t* ticks) 
   return PF_OK;
 }
 
+// fold the recorded event pairs into the running sums (synchronises the device)
+static int prof_fold(pf_handle* h) {
+  if (!h->prof_used) return PF_OK;
+  PF_CUDA(h, cudaDeviceSynchronize());
+  for (int i = 0; i < h->prof_used; ++i) {
+    cudaEvent_t* pe = h->prof_ev + 5 * i;
+    float ms = 0.f;
+    PF_CUDA(h, cudaEventElapsedTime(&ms, pe[0], pe[1]));
+    h->prof.deposit_ms += ms;
+    PF_CUDA(h, cudaEventElapsedTime(&ms, pe[1], pe[2]));
+    h->prof.stencil_ms += ms;
+    if (h->prof_has_agents[i]) {
+      PF_CUDA(h, cudaEventElapsedTime(&ms, pe[3], pe[4]));
+      h->prof.agents_ms += ms;
+    }
+    h->prof.ticks++;
+  }
+  h->prof_used = 0;
+  return PF_OK;
+}
+
+extern "C" int pf_profile_enable(pf_handle* h, int on) {
+  if (!h) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (on && !h->prof_ev) {
+    h->prof_ev = new (std::nothrow) cudaEvent_t[kProfSlots * 5];
+    if (!h->prof_ev) return set_err(h, PF_ENOMEM, "host allocation failed");
+    for (int i = 0; i < kProfSlots * 5; ++i) PF_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
+  }
+  if (!on) { int rc = prof_fold(h); if (rc) return rc; }
+  h->prof_on = on ? 1 : 0;
+  return PF_OK;
+}
+
+extern "C" int pf_profile_read(pf_handle* h, pf_profile* out, int reset) {
+  if (!h || !out) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  int rc = prof_fold(h);
+  if (rc) return rc;
+  *out = h->prof;
+  if (reset) memset(&h->prof, 0, sizeof(h->prof));
+  return PF_OK;
+}
+
+extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t mask, void* stream);
+
+extern "C" int pf_agents_observe(pf_handle* h, const pf_agents* a, const float* x_new, const float* y_new,
+                                 const float* theta_new, void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (a->n == 0) return PF_OK;
+  if (!x_new || !y_new) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_agents_observe<<<blocks_for(a->n, 256), 256, 0, (cudaStream_t)stream>>>(h->dev, a->n, a->x, a->y, a->theta,
+                                                                          a->meta, x_new, y_new, theta_new);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
 extern "C" int pf_step(pf_handle* h, const pf_agents* a, int nsteps, void* stream) {
+  return pf_step_ex(h, a, nsteps, PF_STEP_ALL, stream);
+}
+
+extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t mask, void* stream) {
   int rc = check_agents(h, a);
   if (rc) return rc;
   if (nsteps < 0) return PF_EINVAL;
@@ -579,27 +657,44 @@ extern "C" int pf_step(pf_handle* h, const pf_agents* a, int nsteps, void* strea
   cudaStream_t s = (cudaStream_t)stream;
   for (int t = 0; t < nsteps; ++t) {
     const double now = h->t0 + (double)h->ticks * (double)h->cfg.dt;
-    const bool sense = now >= h->start_delay;
-    const uint32_t flags = PF_STEP_MOVE | (sense ? PF_STEP_SENSE : 0u);
-    if (sense && a->n > 0) {  // deposit_pheromone, sup:577
+    const bool sense = (now >= h->start_delay) && (mask & PF_STEP_SENSE);
+    const uint32_t flags = (mask & PF_STEP_MOVE) | (sense ? PF_STEP_SENSE : 0u);
+    cudaEvent_t* pe = nullptr;
+    if (h->prof_on) {
+      if (h->prof_used == kProfSlots) { rc = prof_fold(h); if (rc) return rc; }
+      pe = h->prof_ev + 5 * h->prof_used;
+      h->prof_has_agents[h->prof_used] = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
+      PF_CUDA(h, cudaEventRecord(pe[0], s));
+    }
+    if (now >= h->start_delay && (mask & PF_STEP_DEPOSIT) && a->n > 0) {  // deposit_pheromone, sup:577
       rc = pf_agents_deposit(h, a, stream);
       if (rc) return rc;
     }
+    if (pe) PF_CUDA(h, cudaEventRecord(pe[1], s));
     // sense/decide/move (side stream) and evaporate+diffuse (main stream) both read the
     // post-deposit field and write disjoint data: run them concurrently
-    if (a->n > 0) {
+    const bool run_agents = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
+    if (run_agents) {
       PF_CUDA(h, cudaEventRecord(h->ev_fork, s));
       PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      if (pe) PF_CUDA(h, cudaEventRecord(pe[3], h->side));
       rc = launch_agents_step(h, a, flags, nullptr, h->side);
       if (rc) return rc;
+      if (pe) PF_CUDA(h, cudaEventRecord(pe[4], h->side));
       PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
     }
-    rc = launch_stencil(h, 0, h->dev.rows, s);
-    if (rc) return rc;
-    if (a->n > 0) PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (mask & PF_STEP_FIELD) {
+      rc = launch_stencil(h, 0, h->dev.rows, s);
+      if (rc) return rc;
+    }
+    if (pe) {
+      PF_CUDA(h, cudaEventRecord(pe[2], s));
+      h->prof_used++;
+    }
+    if (run_agents) PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     k_tick_counter<<<1, 1, 0, s>>>(h->counters);
     PF_LAUNCH_CHECK(h);
-    h->cur ^= 1;
+    if (mask & PF_STEP_FIELD) h->cur ^= 1;
     h->ticks++;
   }
   return PF_OK;
@@ -612,6 +707,42 @@ extern "C" int pf_evaporate_trail(pf_handle* h, int64_t n, const double* elapsed
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   k_evaporate_trail<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, elapsed, intensity, rate, out);
   PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spatial sort of the agent arrays
+// ---------------------------------------------------------------------------------------------
+extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (a->n <= 1) return PF_OK;
+  rc = pf_reserve_agents(h, a->n);
+  if (rc) return rc;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = a->n;
+  uint32_t* keys_in = (uint32_t*)h->scratch;
+  uint32_t* keys_out = keys_in + h->cap;
+  uint32_t* idx_in = keys_out + h->cap;
+  uint32_t* perm = idx_in + h->cap;
+  uint32_t* tmp = perm + h->cap;
+  const unsigned long long cells = (unsigned long long)h->cfg.H * h->cfg.W;
+  if (cells >= 0xffffffffull) return set_err(h, PF_EINVAL, "pf_agents_sort: more than 2^32-1 cells");
+  const uint32_t sentinel = (uint32_t)cells;
+  k_sort_keys<<<blocks_for(n, 256), 256, 0, s>>>(h->dev, n, a->x, a->y, a->meta, keys_in, idx_in, sentinel);
+  PF_LAUNCH_CHECK(h);
+  size_t bytes = h->cub_temp_bytes;
+  PF_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_temp, bytes, keys_in, keys_out, idx_in, perm, (int)n, 0,
+                                             ceil_log2_u64(cells + 1), s));
+  uint32_t* arrays[7] = {(uint32_t*)a->x, (uint32_t*)a->y, (uint32_t*)a->theta, (uint32_t*)a->wl,
+                         (uint32_t*)a->wr, a->meta, a->gid};
+  for (int k = 0; k < 7; ++k) {
+    if (!arrays[k]) continue;
+    k_permute_u32<<<blocks_for(n, 256), 256, 0, s>>>(n, perm, arrays[k], tmp);
+    PF_LAUNCH_CHECK(h);
+    PF_CUDA(h, cudaMemcpyAsync(arrays[k], tmp, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
+  }
   return PF_OK;
 }
 

@@ -112,6 +112,7 @@ class PheroField:
         _ffi.check(self._L.pf_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         self.rows = cfg.row1 - cfg.row0
+        self.start_delay = 0.0
 
     # -- lifecycle
     def close(self):
@@ -211,11 +212,19 @@ class PheroField:
         self._ck(self._L.pf_agents_step(self._h, C.byref(a.struct()), flags, _ptr(decisions),
                                         self._s()))
 
-    def step(self, a: Swarm, nsteps: int = 1):
-        self._ck(self._L.pf_step(self._h, C.byref(a.struct()), nsteps, self._s()))
+    def step(self, a: Swarm, nsteps: int = 1, flags: int = abi.STEP_ALL):
+        self._ck(self._L.pf_step_ex(self._h, C.byref(a.struct()), nsteps, flags, self._s()))
+
+    def observe(self, a: Swarm, x: torch.Tensor, y: torch.Tensor, theta: Optional[torch.Tensor] = None):
+        self._ck(self._L.pf_agents_observe(self._h, C.byref(a.struct()), _ptr(x), _ptr(y), _ptr(theta),
+                                           self._s()))
+
+    def sort_agents(self, a: Swarm):
+        self._ck(self._L.pf_agents_sort(self._h, C.byref(a.struct()), self._s()))
 
     def set_time(self, time_s: float = 0.0, start_delay_s: float = 0.0):
         self._ck(self._L.pf_set_time(self._h, time_s, start_delay_s))
+        self.start_delay = start_delay_s
 
     def time(self):
         t = C.c_double()
@@ -250,6 +259,14 @@ class PheroField:
         n = C.c_uint64()
         self._ck(self._L.pf_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def profile(self, on: bool):
+        self._ck(self._L.pf_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> abi.PFProfile:
+        p = abi.PFProfile()
+        self._ck(self._L.pf_profile_read(self._h, C.byref(p), 1 if reset else 0))
+        return p
 
     def set_stencil_variant(self, variant: int, rows_per_cta: int = 0):
         self._ck(self._L.pf_set_stencil_variant(self._h, variant, rows_per_cta))

@@ -1,0 +1,103 @@
+"""Test-only backend for swarm_robotics_pheromones_b200.sharded: the CPU oracle as the per-strip
+compute engine, numpy memory shared with CPU torch tensors so gloo can move the bytes."""
+import numpy as np
+import torch
+
+from oracle import dense
+from swarm_robotics_pheromones_b200 import abi
+
+W8 = abi.PF_MIGRATE_WORDS
+
+
+class OracleStrip:
+    def __init__(self, cfg, x, y, theta, state, gid, capacity, migrate_cap):
+        self.cfg = cfg
+        self.o = dense.DenseOracle(cfg)
+        self.rows = cfg.row1 - cfg.row0
+        n = len(x)
+        pad = capacity - n
+        z = np.zeros(pad, np.float32)
+        self.a = dense.AgentsNP(np.concatenate([x, z]), np.concatenate([y, z]),
+                                np.concatenate([theta, z]),
+                                np.concatenate([np.asarray(state, np.int64), np.zeros(pad, np.int64)]),
+                                np.concatenate([np.asarray(gid, np.uint32), np.zeros(pad, np.uint32)]))
+        self.a.meta[n:] = abi.STATE_EMPTY
+        self.mcap = migrate_cap
+        words = W8 * (migrate_cap + 1)
+        self.send_up = torch.zeros(words, dtype=torch.int32)
+        self.send_down = torch.zeros(words, dtype=torch.int32)
+        self.recv_up = torch.zeros(words, dtype=torch.int32)
+        self.recv_down = torch.zeros(words, dtype=torch.int32)
+
+    def _rows(self, idx):
+        v = self.o.field_with_ghosts
+        return [torch.from_numpy(v[c, idx]) for c in range(self.cfg.C)]
+
+    def edge_rows(self):
+        return self._rows(1), self._rows(self.rows)
+
+    def ghost_rows(self):
+        return self._rows(0), self._rows(self.rows + 1)
+
+    def deposit(self):
+        self.o.agents_deposit(self.a)
+
+    def field_rows(self, r0, r1):
+        # the oracle steps whole strips: do it once, on the first call of the tick
+        if not getattr(self, "_stepped", False):
+            import ctypes as C
+            self.o.fill_ghosts()  # reflect rows at the arena's outer edges only
+            dense.lib().po_step_field(C.byref(self.o.cfg), dense._fp(self.o.bufs[self.o.cur]),
+                                      dense._fp(self.o.bufs[self.o.cur ^ 1]))
+            self._stepped = True
+
+    def agents(self, flags):
+        self.o.agents_step(self.a, flags)
+
+    def swap(self):
+        self.o.cur ^= 1
+        self._stepped = False
+
+    def pack(self):
+        a = self.a
+        r, _, _ = dense.cells_of(self.cfg, a.x, a.y)
+        alive = (a.meta & 3) != 0
+        for buf, mask in ((self.send_up, alive & (r < self.cfg.row0)),
+                          (self.send_down, alive & (r >= self.cfg.row1))):
+            idx = np.nonzero(mask)[0][: self.mcap]
+            out = buf.numpy().view(np.uint32)
+            out[:] = 0
+            out[0] = len(idx)
+            rec = out[W8:].reshape(-1, W8)
+            for k, f in enumerate(("x", "y", "theta", "wl", "wr")):
+                rec[: len(idx), k] = getattr(a, f)[idx].view(np.uint32)
+            rec[: len(idx), 5] = a.meta[idx]
+            rec[: len(idx), 6] = a.gid[idx]
+            a.meta[idx] = abi.STATE_EMPTY
+
+    def unpack(self, from_up, from_down):
+        a = self.a
+        for use, buf in ((from_up, self.recv_up), (from_down, self.recv_down)):
+            if not use:
+                continue
+            inp = buf.numpy().view(np.uint32)
+            m = int(inp[0])
+            rec = inp[W8:].reshape(-1, W8)[:m]
+            empty = np.nonzero((a.meta & 3) == 0)[0][:m]
+            assert len(empty) == m, "no empty slot left"
+            for k, f in enumerate(("x", "y", "theta", "wl", "wr")):
+                getattr(a, f)[empty] = rec[:, k].view(np.float32)
+            a.meta[empty] = rec[:, 5]
+            a.gid[empty] = rec[:, 6]
+
+    def synchronize(self):
+        pass
+
+
+def gather_agents_sorted(parts):
+    """concatenate alive agents of several AgentsNP-like dicts and sort by gid"""
+    cat = {f: np.concatenate([p[f] for p in parts]) for f in dense.AgentsNP.FIELDS}
+    alive = (cat["meta"] & 3) != 0
+    cat = {f: v[alive] for f, v in cat.items()}
+    order = np.argsort(cat["gid"], kind="stable")
+    return {f: v[order] for f, v in cat.items()}

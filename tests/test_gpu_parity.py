@@ -391,3 +391,35 @@ def test_evaporate_trail_known_answers(golden_dir):
     for want, nticks in zip(lv[:4], (14, 13, 12, 11)):
         assert abs(vals[nticks - 1] - want) < 1e-12
     g.close()
+
+
+def test_agents_sort_keeps_results_by_gid():
+    # physical re-ordering by cell: same agents (by gid), same field, as the unsorted oracle run
+    cfg = make_cfg(256, 512, 2, 9, D=0.1)
+    cfg.fsm = 1
+    rng = np.random.default_rng(31)
+    n = 20000
+    x, y, th, _ = rand_agents(rng, cfg, n, margin=0.05)
+    st = rng.integers(1, 3, n)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    sw = Swarm(x, y, th, st, capacity=n + 100)  # trailing empty slots must stay last
+    for rounds in range(4):
+        g.sort_agents(sw)
+        got = sw.to_numpy()
+        alive = (got["meta"] & 3) != 0
+        assert alive[:n].all() and not alive[n:].any()
+        r, q, _ = dense.cells_of(cfg, got["x"][:n], got["y"][:n])
+        key = r * cfg.W + q
+        assert (np.diff(key) >= 0).all(), "agents not ordered by cell"
+        o.tick(a_np, 25)
+        g.step(sw, 25)
+        got = sw.to_numpy()
+        order = np.argsort(got["gid"][:n], kind="stable")
+        assert (got["gid"][:n][order] == a_np.gid).all()
+        for f in ("x", "y", "theta", "wl", "wr"):
+            assert_bitexact(got[f][:n][order], getattr(a_np, f), f)
+        assert (got["meta"][:n][order] == a_np.meta).all()
+        assert_bitexact(g.snapshot(), o.field, "field after sorted ticks")
+    g.close()
