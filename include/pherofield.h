@@ -302,8 +302,12 @@ typedef struct pf_profile {
 int pf_profile_enable(pf_handle* h, int on);
 int pf_profile_read(pf_handle* h, pf_profile* out_host, int reset);
 
+/* tuning options */
+#define PF_OPT_OVERLAP_AGENTS 1 /* pf_step: run sense/decide/move on a side stream beside the stencil */
+int pf_set_option(pf_handle* h, int option, int value);
+
 /* which stencil kernel variant pf_step_field uses: 0 = auto, 1 = register sliding window (LDG),
- * 2 = TMA + mbarrier pipelined shared-memory tiles. For tuning sweeps. */
+ * 2..5 = TMA + mbarrier pipelined shared-memory ring (4x4, 8x3, 2x8, 4x6 rows x stages). */
 int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_cta);
 
 #ifdef __cplusplus

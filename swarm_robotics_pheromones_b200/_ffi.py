@@ -50,6 +50,7 @@ SIGNATURES = {
     "pf_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "pf_profile_enable": (C.c_int, [_vp, C.c_int]),
     "pf_profile_read": (C.c_int, [_vp, C.POINTER(abi.PFProfile), C.c_int]),
+    "pf_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "pf_set_stencil_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
 }
 

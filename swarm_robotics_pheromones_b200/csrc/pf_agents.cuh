@@ -15,9 +15,15 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
                       const float* __restrict__ y, uint32_t* __restrict__ meta,
                       uint32_t* __restrict__ keys, float* __restrict__ vals, uint32_t sentinel,
                       unsigned long long* __restrict__ counters) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool dep = false;
-  if (i < n) {
+  // grid-stride over a fixed grid (a multiple of the SM count): the deposit counter costs one
+  // global atomic per CTA instead of one per warp (same-address atomics serialise in L2)
+  __shared__ unsigned int s_dep;
+  if (threadIdx.x == 0) s_dep = 0;
+  __syncthreads();
+  unsigned int ndep = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    bool dep = false;
     uint32_t mt = meta[i];
     uint32_t st = mt & PF_META_STATE_MASK;
     uint32_t key = sentinel;
@@ -37,9 +43,12 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
     }
     keys[i] = key;
     vals[i] = amt;
+    ndep += dep ? 1u : 0u;
   }
-  unsigned m = __ballot_sync(0xffffffffu, dep);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[1], (unsigned long long)__popc(m));
+  ndep = __reduce_add_sync(0xffffffffu, ndep);
+  if ((threadIdx.x & 31) == 0 && ndep) atomicAdd(&s_dep, ndep);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_dep) atomicAdd(&counters[1], (unsigned long long)s_dep);
 }
 
 // generic positions/amounts (pf_deposit)
@@ -207,8 +216,9 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
   __shared__ unsigned int hist[8];
   if (threadIdx.x < 8) hist[threadIdx.x] = 0;
   __syncthreads();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
+  // grid-stride over a fixed grid: the decision histogram is flushed once per CTA
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
     uint32_t mt = ameta[i];
     uint32_t st = mt & PF_META_STATE_MASK;
     if (st == PF_STATE_EMPTY) {
@@ -333,7 +343,11 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
           atomicAdd(&hist[7], 1u);
         }
       }
-      atomicAdd(&hist[dec], 1u);
+      {  // warp-aggregated histogram update: one shared atomic per distinct decision per warp
+        unsigned act = __activemask();
+        unsigned peers = __match_any_sync(act, dec);
+        if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[dec], (unsigned)__popc(peers));
+      }
       ax[i] = x;
       ay[i] = y;
       ath[i] = th;

@@ -42,6 +42,8 @@ struct pf_handle {
   double t0, start_delay;
   uint64_t ticks;
   int variant, rows_per_cta;
+  int overlap_agents;
+  int n_sm, wave_keys, wave_agents;
   TmaStencilState tma;
   // profiling: ring of per-tick events
   int prof_on;
@@ -82,6 +84,12 @@ static int set_err(pf_handle* h, int code, const char* fmt, ...) {
 
 static inline unsigned blocks_for(long long n, int threads) {
   return (unsigned)((n + threads - 1) / threads);
+}
+// grid for the grid-stride agent kernels: exactly one resident wave (SMs x CTAs/SM from the
+// occupancy calculator), so no partial second wave
+static inline unsigned wave_grid(long long n, int wave) {
+  unsigned b = blocks_for(n, 256);
+  return b < (unsigned)wave ? b : (unsigned)wave;
 }
 
 static int ceil_log2_u64(unsigned long long v) {
@@ -245,6 +253,14 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  {
+    int occ = 0;
+    CREATE_CUDA(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_deposit_keys_agents, 256, 0));
+    h->wave_keys = h->n_sm * (occ > 0 ? occ : 1);
+    CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_agents_step, 256, 0));
+    h->wave_agents = h->n_sm * (occ > 0 ? occ : 1);
+  }
   CREATE_CUDA(cudaDeviceSynchronize());
 #undef CREATE_CUDA
   h->variant = 0;
@@ -268,7 +284,7 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->prof_ev) {
-    for (int i = 0; i < kProfSlots * 5; ++i) cudaEventDestroy(h->prof_ev[i]);
+    for (int i = 0; i < kProfSlots * 6; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;
   }
   delete h;
@@ -472,6 +488,12 @@ extern "C" int pf_swap(pf_handle* h) {
   return PF_OK;
 }
 
+extern "C" int pf_set_option(pf_handle* h, int option, int value) {
+  if (!h) return PF_EINVAL;
+  if (option == PF_OPT_OVERLAP_AGENTS) { h->overlap_agents = value ? 1 : 0; return PF_OK; }
+  return set_err(h, PF_EINVAL, "unknown option %d", option);
+}
+
 extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_cta) {
   if (!h || variant < 0 || variant > 5 || rows_per_cta < 0) return PF_EINVAL;
   h->variant = variant;
@@ -531,7 +553,7 @@ extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream)
   cudaStream_t s = (cudaStream_t)stream;
   uint32_t* keys_in = (uint32_t*)h->scratch;
   float* vals_in = (float*)(keys_in + 2 * h->cap);
-  k_deposit_keys_agents<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, keys_in,
+  k_deposit_keys_agents<<<wave_grid(a->n, h->wave_keys), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, keys_in,
                                                              vals_in, h->sentinel, h->counters);
   PF_LAUNCH_CHECK(h);
   return sort_and_sum(h, a->n, s);
@@ -553,7 +575,7 @@ extern "C" int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y,
 }
 
 static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s) {
-  k_agents_step<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, h->buf[h->cur], flags, a->n, a->x, a->y,
+  k_agents_step<<<wave_grid(a->n, h->wave_agents), 256, 0, s>>>(h->dev, h->buf[h->cur], flags, a->n, a->x, a->y,
                                                      a->theta, a->wl, a->wr, a->meta, dec, h->counters);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
@@ -588,11 +610,11 @@ static int prof_fold(pf_handle* h) {
   if (!h->prof_used) return PF_OK;
   PF_CUDA(h, cudaDeviceSynchronize());
   for (int i = 0; i < h->prof_used; ++i) {
-    cudaEvent_t* pe = h->prof_ev + 5 * i;
+    cudaEvent_t* pe = h->prof_ev + 6 * i;
     float ms = 0.f;
     PF_CUDA(h, cudaEventElapsedTime(&ms, pe[0], pe[1]));
     h->prof.deposit_ms += ms;
-    PF_CUDA(h, cudaEventElapsedTime(&ms, pe[1], pe[2]));
+    PF_CUDA(h, cudaEventElapsedTime(&ms, pe[5], pe[2]));
     h->prof.stencil_ms += ms;
     if (h->prof_has_agents[i]) {
       PF_CUDA(h, cudaEventElapsedTime(&ms, pe[3], pe[4]));
@@ -608,9 +630,9 @@ extern "C" int pf_profile_enable(pf_handle* h, int on) {
   if (!h) return PF_EINVAL;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   if (on && !h->prof_ev) {
-    h->prof_ev = new (std::nothrow) cudaEvent_t[kProfSlots * 5];
+    h->prof_ev = new (std::nothrow) cudaEvent_t[kProfSlots * 6];
     if (!h->prof_ev) return set_err(h, PF_ENOMEM, "host allocation failed");
-    for (int i = 0; i < kProfSlots * 5; ++i) PF_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
+    for (int i = 0; i < kProfSlots * 6; ++i) PF_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
   }
   if (!on) { int rc = prof_fold(h); if (rc) return rc; }
   h->prof_on = on ? 1 : 0;
@@ -662,7 +684,7 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
     cudaEvent_t* pe = nullptr;
     if (h->prof_on) {
       if (h->prof_used == kProfSlots) { rc = prof_fold(h); if (rc) return rc; }
-      pe = h->prof_ev + 5 * h->prof_used;
+      pe = h->prof_ev + 6 * h->prof_used;
       h->prof_has_agents[h->prof_used] = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
       PF_CUDA(h, cudaEventRecord(pe[0], s));
     }
@@ -674,15 +696,23 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
     // sense/decide/move (side stream) and evaporate+diffuse (main stream) both read the
     // post-deposit field and write disjoint data: run them concurrently
     const bool run_agents = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
+    // Measured on B200 (profiles/r01a_*): overlapped, the agent kernel is starved behind the
+    // stencil's CTAs and the pair takes 4.55 ms against 0.63 + 2.65 ms back to back, so the
+    // default is back to back on the caller's stream; PF_OPT_OVERLAP_AGENTS restores the fork.
+    const bool fork = run_agents && h->overlap_agents;
+    cudaStream_t as = fork ? h->side : s;
     if (run_agents) {
-      PF_CUDA(h, cudaEventRecord(h->ev_fork, s));
-      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-      if (pe) PF_CUDA(h, cudaEventRecord(pe[3], h->side));
-      rc = launch_agents_step(h, a, flags, nullptr, h->side);
+      if (fork) {
+        PF_CUDA(h, cudaEventRecord(h->ev_fork, s));
+        PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      }
+      if (pe) PF_CUDA(h, cudaEventRecord(pe[3], as));
+      rc = launch_agents_step(h, a, flags, nullptr, as);
       if (rc) return rc;
-      if (pe) PF_CUDA(h, cudaEventRecord(pe[4], h->side));
-      PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+      if (pe) PF_CUDA(h, cudaEventRecord(pe[4], as));
+      if (fork) PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
     }
+    if (pe) PF_CUDA(h, cudaEventRecord(pe[5], s));
     if (mask & PF_STEP_FIELD) {
       rc = launch_stencil(h, 0, h->dev.rows, s);
       if (rc) return rc;
@@ -691,7 +721,7 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
       PF_CUDA(h, cudaEventRecord(pe[2], s));
       h->prof_used++;
     }
-    if (run_agents) PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (fork) PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     k_tick_counter<<<1, 1, 0, s>>>(h->counters);
     PF_LAUNCH_CHECK(h);
     if (mask & PF_STEP_FIELD) h->cur ^= 1;

@@ -268,5 +268,8 @@ class PheroField:
         self._ck(self._L.pf_profile_read(self._h, C.byref(p), 1 if reset else 0))
         return p
 
+    def set_option(self, option: int, value: int):
+        self._ck(self._L.pf_set_option(self._h, option, value))
+
     def set_stencil_variant(self, variant: int, rows_per_cta: int = 0):
         self._ck(self._L.pf_set_stencil_variant(self._h, variant, rows_per_cta))

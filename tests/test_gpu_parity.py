@@ -334,6 +334,22 @@ def test_tick_two_channel_fsm_foraging():
     g.close()
 
 
+def test_tick_overlapped_agent_stream_same_result():
+    cfg = make_cfg(256, 1024, 2, 5)
+    rng = np.random.default_rng(77)
+    x, y, th, _ = rand_agents(rng, cfg, 5000, margin=0.05)
+    a_np = dense.AgentsNP(x, y, th)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    g.set_option(abi.OPT_OVERLAP_AGENTS, 1)
+    sw = Swarm(x, y, th)
+    o.tick(a_np, 40)
+    g.step(sw, 40)
+    _compare_agents(sw, a_np)
+    assert_bitexact(g.snapshot(), o.field)
+    g.close()
+
+
 def test_tick_start_delay_random_walk():
     # before t = 5 s no deposit and no sensing (sup:731-744); 100 ticks cross the 5 s mark at 79
     cfg = make_cfg(128, 256, 1, 5)
