@@ -367,6 +367,7 @@ def run_sharded(args):
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = os.environ.get("PF_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
     scfg = sharded.strip_config(cfg, world, rank, device=local)
@@ -385,10 +386,19 @@ def run_sharded(args):
     drv = sharded.DistDriver(worker, overlap=not args.no_overlap)
     cells = cfg.H * cfg.W * cfg.C
 
-    for _ in range(args.warmup):
+    tick_no = [0]
+
+    def tick():
+        if args.sort_every > 0 and tick_no[0] % args.sort_every == 0:
+            strip.sort_agents()
         drv.tick(True)
+        tick_no[0] += 1
+
+    for _ in range(args.warmup):
+        tick()
     torch.cuda.synchronize()
     dist.barrier()
+    tick_no[0] = 0  # the timed region pays ceil(K / sort_every) sorts
     sampler = ClockSampler(local)
     l0 = strip.field.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -396,7 +406,7 @@ def run_sharded(args):
     torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        drv.tick(True)
+        tick()
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -478,6 +488,7 @@ def run_sharded(args):
             "cpu_baseline": None,
             "agents_per_rank": [int(c.item()) for c in allc],
             "halo_overlap": not args.no_overlap, "stencil_variant": args.variant,
+            "agent_sort_every": args.sort_every,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

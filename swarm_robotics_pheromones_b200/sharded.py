@@ -72,16 +72,25 @@ class CudaStrip:
         self.recv_down = torch.zeros(words, dtype=torch.int32, device=dev)  # from rank+1
         self.field.reserve_agents(capacity)
 
-    # halo tensors: lists of contiguous [W] rows, one per channel
+    # halo tensors: lists of contiguous [W] rows, one per channel. The two buffers never move, so
+    # the row views of both are built once and selected by the swap parity.
+    def _rows_cache(self):
+        if getattr(self, "_cache", None) is None:
+            C, rows = self.cfg.C, self.rows
+            both = []
+            for which in (0, 1):
+                v = self.field.view(which, with_ghosts=True)
+                both.append({"edge": ([v[c, 1] for c in range(C)], [v[c, rows] for c in range(C)]),
+                             "ghost": ([v[c, 0] for c in range(C)], [v[c, rows + 1] for c in range(C)])})
+            self._cache = both
+            self._parity = 0
+        return self._cache[self._parity]
+
     def edge_rows(self):
-        v = self.field.view(0, with_ghosts=True)
-        C = self.cfg.C
-        return [v[c, 1] for c in range(C)], [v[c, self.rows] for c in range(C)]
+        return self._rows_cache()["edge"]
 
     def ghost_rows(self):
-        v = self.field.view(0, with_ghosts=True)
-        C = self.cfg.C
-        return [v[c, 0] for c in range(C)], [v[c, self.rows + 1] for c in range(C)]
+        return self._rows_cache()["ghost"]
 
     def deposit(self):
         self.field.agents_deposit(self.swarm)
@@ -94,6 +103,11 @@ class CudaStrip:
 
     def swap(self):
         self.field.swap()
+        if getattr(self, "_cache", None) is not None:
+            self._parity ^= 1
+
+    def sort_agents(self):
+        self.field.sort_agents(self.swarm)
 
     def pack(self):
         self.field.migrate_pack(self.swarm, self.send_up, self.send_down, self.mcap)

@@ -1,0 +1,105 @@
+"""Multi-GPU parity under torchrun (NCCL): G row strips on G GPUs vs the unsharded run on rank 0's
+GPU, bit for bit (field and agents by gid).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dist_parity.py --ticks 100
+"""
+import argparse
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from swarm_robotics_pheromones_b200 import abi, sharded  # noqa: E402
+from swarm_robotics_pheromones_b200.field import PheroField, Swarm  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--ticks", type=int, default=100)
+ap.add_argument("--grid", type=int, default=2048)
+ap.add_argument("--agents", type=int, default=200000)
+ap.add_argument("--no-overlap", action="store_true")
+args = ap.parse_args()
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+H = W = args.grid
+cfg = abi.default_config(H, W, 2)
+cfg.stencil = 9
+cfg.fsm = 1
+for c in range(2):
+    cfg.diffusion[c] = 0.1
+    cfg.evap_keep[c] = 0.95
+cfg.nest_x, cfg.nest_y = 0.5 * H * 0.01, 0.5 * W * 0.01
+cfg.food_x[0], cfg.food_y[0] = 0.7 * H * 0.01, 0.6 * W * 0.01
+cfg.food_radius = 0.5
+rng = np.random.default_rng(42)
+n = args.agents
+x = rng.uniform(0.05, H * 0.01 - 0.05, n).astype(np.float32)
+y = rng.uniform(0.05, W * 0.01 - 0.05, n).astype(np.float32)
+th = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+st = rng.integers(1, 3, n)
+
+parts = sharded.partition_agents(cfg, world, x, y, th, st)
+p = parts[rank]
+scfg = sharded.strip_config(cfg, world, rank, device=local)
+strip = sharded.CudaStrip(scfg, p["x"], p["y"], p["theta"], p["state"], p["gid"],
+                          capacity=int(len(p["x"]) * 1.5) + 1024, migrate_cap=8192)
+drv = sharded.DistDriver(sharded.StripWorker(strip, rank, world), overlap=not args.no_overlap)
+for _ in range(args.ticks):
+    drv.tick(True)
+torch.cuda.synchronize()
+
+# gather strips on rank 0
+field_local = torch.from_numpy(strip.field.snapshot()).cuda()
+sizes = [sharded.strip_bounds(H, world, r) for r in range(world)]
+sw = strip.swarm.to_numpy()
+alive = (sw["meta"] & 3) != 0
+rec = np.stack([sw[f][alive].view(np.uint32) for f in ("gid", "x", "y", "theta", "wl", "wr", "meta")], 1)
+counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+dist.all_gather(counts, torch.tensor([rec.shape[0]], dtype=torch.int64, device="cuda"))
+ok = True
+if rank == 0:
+    fields = [field_local]
+    recs = [rec]
+    for r in range(1, world):
+        rows = sizes[r][1] - sizes[r][0]
+        buf = torch.empty((2, rows, W), dtype=torch.float32, device="cuda")
+        dist.recv(buf, r)
+        fields.append(buf)
+        rb = torch.empty((int(counts[r].item()), 7), dtype=torch.int32, device="cuda")
+        dist.recv(rb, r)
+        recs.append(rb.cpu().numpy().view(np.uint32))
+    field = torch.cat(fields, 1).cpu().numpy()
+    allrec = np.concatenate(recs)
+    allrec = allrec[np.argsort(allrec[:, 0], kind="stable")]
+    # unsharded run on this GPU
+    g = PheroField(cfg)
+    s1 = Swarm(x, y, th, st)
+    g.step(s1, args.ticks)
+    torch.cuda.synchronize()
+    want_f = g.snapshot()
+    w = s1.to_numpy()
+    same_field = bool((field.view(np.uint32) == want_f.view(np.uint32)).all())
+    same_n = allrec.shape[0] == n
+    same_agents = same_n and all(
+        (allrec[:, k + 1] == w[f].view(np.uint32)).all()
+        for k, f in enumerate(("x", "y", "theta", "wl", "wr", "meta")))
+    mig = strip.field.counters()
+    ok = same_field and same_agents
+    print(f"dist_parity world={world} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
+          f"agents_bitexact={same_agents} (rank0 migrated_out={mig.migrated_out}, dropped={mig.migrate_dropped}) "
+          f"-> {'PASS' if ok else 'FAIL'}", flush=True)
+else:
+    dist.send(field_local, 0)
+    dist.send(torch.from_numpy(rec.view(np.int32)).cuda(), 0)
+dist.barrier()
+strip.field.close()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
