@@ -303,6 +303,8 @@ def run_single(args):
     st_ms = prof.stencil_ms / max(1, prof.ticks)
     ach = cells * BYTES_PER_CELL_UPDATE / (st_ms * 1e-3) / 1e9
     tr = stencil_traffic_from_profile()
+    if tr and (tr.get("cells") != cells or tr.get("stencil") != cfg.stencil):
+        tr = None  # the committed ncu capture is for another shape
     roofline = {"bound": "hbm", "kernel": "evaporate+diffuse stencil", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                 "frac_of_8TBs_nominal": ach / 8000.0,
