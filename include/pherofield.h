@@ -284,6 +284,10 @@ int pf_migrate_pack(pf_handle* h, const pf_agents* a, uint32_t* up_buf, uint32_t
 /* Append the records of a received buffer into empty slots (lowest slot first, deterministic). */
 int pf_migrate_unpack(pf_handle* h, const pf_agents* a, const uint32_t* buf, int64_t cap,
                       void* stream);
+/* Same for two received buffers in one pass: all records of `buf`, then all of `buf2` (either may
+ * be NULL). */
+int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32_t* buf, const uint32_t* buf2,
+                       int64_t cap, void* stream);
 
 int pf_counters_host(pf_handle* h, pf_counters* out_host, void* stream);
 int pf_counters_reset(pf_handle* h, void* stream);

@@ -45,6 +45,7 @@ SIGNATURES = {
     "pf_evaporate_trail": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_double, _vp, _vp]),
     "pf_migrate_pack": (C.c_int, [_vp, _agp, _vp, _vp, C.c_int64, _vp]),
     "pf_migrate_unpack": (C.c_int, [_vp, _agp, _vp, C.c_int64, _vp]),
+    "pf_migrate_unpack2": (C.c_int, [_vp, _agp, _vp, _vp, C.c_int64, _vp]),
     "pf_counters_host": (C.c_int, [_vp, C.POINTER(abi.PFCounters), _vp]),
     "pf_counters_reset": (C.c_int, [_vp, _vp]),
     "pf_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),

@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(256)
 k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
               float* __restrict__ ax, float* __restrict__ ay, float* __restrict__ ath,
               float* __restrict__ awl, float* __restrict__ awr, uint32_t* __restrict__ ameta,
-              uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters) {
+              uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters,
+              unsigned long long* __restrict__ mig_flags) {
   __shared__ unsigned int hist[8];
   if (threadIdx.x < 8) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -223,6 +224,7 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
     uint32_t st = mt & PF_META_STATE_MASK;
     if (st == PF_STATE_EMPTY) {
       if (dec_out) dec_out[i] = PF_DEC_NONE;
+      if (mig_flags) mig_flags[i] = 0ull;
     } else {
       float x = ax[i], y = ay[i], th = ath[i], wl = awl[i], wr = awr[i];
       int dec = PF_DEC_NONE;
@@ -356,6 +358,11 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
       ameta[i] = (mt & ~(PF_META_STATE_MASK | PF_META_MOVED | PF_META_DEC_MASK | PF_META_CARRY)) |
                  st | moved | ((uint32_t)dec << PF_META_DEC_SHIFT) | carry;
       if (dec_out) dec_out[i] = (uint8_t)dec;
+      if (mig_flags) {  // same rule as k_migrate_flags: did the (new) cell row leave the strip?
+        int r, q;
+        pf_cell(p, x, y, r, q);
+        mig_flags[i] = (r < p.row0) ? 1ull : ((r >= p.row1) ? (1ull << 32) : 0ull);
+      }
     }
   }
   __syncthreads();
@@ -453,12 +460,17 @@ k_empty_flags(long long n, const uint32_t* __restrict__ meta, unsigned long long
 __global__ void __launch_bounds__(256)
 k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
                const unsigned long long* __restrict__ ranks, const uint32_t* __restrict__ buf,
-               long long cap, float* ax, float* ay, float* ath, float* awl, float* awr,
-               uint32_t* ameta, uint32_t* agid, unsigned long long* __restrict__ counters) {
+               const uint32_t* __restrict__ buf2, long long cap, float* ax, float* ay, float* ath,
+               float* awl, float* awr, uint32_t* ameta, uint32_t* agid,
+               unsigned long long* __restrict__ counters) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long m = buf[0];
-  if (m > (unsigned long long)cap) m = cap;
+  // records of `buf` first, then those of `buf2` (either may be absent)
+  unsigned long long m1 = buf ? buf[0] : 0ull;
+  if (m1 > (unsigned long long)cap) m1 = cap;
+  unsigned long long m2 = buf2 ? buf2[0] : 0ull;
+  if (m2 > (unsigned long long)cap) m2 = cap;
+  const unsigned long long m = m1 + m2;
   if (i == n - 1) {
     unsigned long long empties = ranks[i] + flags[i];
     unsigned long long placed = m < empties ? m : empties;
@@ -468,7 +480,7 @@ k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
   if (!flags[i]) return;
   unsigned long long r = ranks[i];
   if (r >= m) return;
-  const uint32_t* rec = buf + (r + 1) * kMigWords;
+  const uint32_t* rec = (r < m1) ? buf + (r + 1) * kMigWords : buf2 + (r - m1 + 1) * kMigWords;
   ax[i] = __uint_as_float(rec[0]);
   ay[i] = __uint_as_float(rec[1]);
   ath[i] = __uint_as_float(rec[2]);

@@ -44,6 +44,8 @@ struct pf_handle {
   int variant, rows_per_cta;
   int overlap_agents;
   int n_sm, wave_keys, wave_agents;
+  long long mig_flags_n;   // > 0: scratch holds the migration flags the last move kernel wrote
+  const float* mig_flags_x;
   TmaStencilState tma;
   // profiling: ring of per-tick events
   int prof_on;
@@ -81,6 +83,8 @@ static int set_err(pf_handle* h, int code, const char* fmt, ...) {
                      cudaGetErrorString(e__), __FILE__, __LINE__);                  \
     (h)->launches++;                                                                \
   } while (0)
+
+static bool is_sharded(const pf_handle* h) { return h->cfg.row0 > 0 || h->cfg.row1 < h->cfg.H; }
 
 static inline unsigned blocks_for(long long n, int threads) {
   return (unsigned)((n + threads - 1) / threads);
@@ -306,7 +310,7 @@ extern "C" int pf_reserve_agents(pf_handle* h, int64_t max_agents) {
   PF_CUDA(h, cudaDeviceSynchronize());
   if (h->scratch) cudaFree(h->scratch);
   if (h->cub_temp) cudaFree(h->cub_temp);
-  h->scratch = nullptr; h->cub_temp = nullptr; h->cap = 0;
+  h->scratch = nullptr; h->cub_temp = nullptr; h->cap = 0; h->mig_flags_n = 0;
   long long cap = (max_agents + 1023) / 1024 * 1024;
   PF_CUDA(h, cudaMalloc(&h->scratch, (size_t)cap * 20));  // + 4 B/agent for the permute pass
   size_t sort_bytes = 0, scan_bytes = 0;
@@ -461,7 +465,6 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) 
   return PF_OK;
 }
 
-static bool is_sharded(const pf_handle* h) { return h->cfg.row0 > 0 || h->cfg.row1 < h->cfg.H; }
 
 extern "C" int pf_step_field(pf_handle* h, int nsteps, void* stream) {
   if (!h || nsteps < 0) return PF_EINVAL;
@@ -505,6 +508,7 @@ extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_ct
 // K2 launch
 // ---------------------------------------------------------------------------------------------
 static int sort_and_sum(pf_handle* h, long long n, cudaStream_t s) {
+  h->mig_flags_n = 0;  // the sort reuses the scratch the migration flags live in
   uint32_t* keys_in = (uint32_t*)h->scratch;
   uint32_t* keys_out = keys_in + h->cap;
   float* vals_in = (float*)(keys_out + h->cap);
@@ -575,8 +579,15 @@ extern "C" int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y,
 }
 
 static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s) {
+  // on a strip, the move kernel also emits the leave-up / leave-down flags pf_migrate_pack needs
+  unsigned long long* mig = nullptr;
+  if (is_sharded(h) && (flags & PF_STEP_MOVE) && h->scratch && a->n <= h->cap) {
+    mig = (unsigned long long*)h->scratch;
+    h->mig_flags_n = a->n;
+    h->mig_flags_x = a->x;
+  }
   k_agents_step<<<wave_grid(a->n, h->wave_agents), 256, 0, s>>>(h->dev, h->buf[h->cur], flags, a->n, a->x, a->y,
-                                                     a->theta, a->wl, a->wr, a->meta, dec, h->counters);
+                                                     a->theta, a->wl, a->wr, a->meta, dec, h->counters, mig);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -650,6 +661,8 @@ extern "C" int pf_profile_read(pf_handle* h, pf_profile* out, int reset) {
 }
 
 extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t mask, void* stream);
+extern "C" int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32_t* buf, const uint32_t* buf2,
+                                  int64_t cap, void* stream);
 
 extern "C" int pf_agents_observe(pf_handle* h, const pf_agents* a, const float* x_new, const float* y_new,
                                  const float* theta_new, void* stream) {
@@ -752,6 +765,7 @@ extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = a->n;
+  h->mig_flags_n = 0;
   uint32_t* keys_in = (uint32_t*)h->scratch;
   uint32_t* keys_out = keys_in + h->cap;
   uint32_t* idx_in = keys_out + h->cap;
@@ -795,8 +809,11 @@ extern "C" int pf_migrate_pack(pf_handle* h, const pf_agents* a, uint32_t* up_bu
   if (rc) return rc;
   unsigned long long* flags = (unsigned long long*)h->scratch;
   unsigned long long* ranks = flags + h->cap;
-  k_migrate_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, flags);
-  PF_LAUNCH_CHECK(h);
+  if (h->mig_flags_n != a->n || h->mig_flags_x != a->x) {
+    k_migrate_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, flags);
+    PF_LAUNCH_CHECK(h);
+  }
+  h->mig_flags_n = 0;
   size_t bytes = h->cub_temp_bytes;
   PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
   k_migrate_scatter<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, cap, flags, ranks, a->x, a->y, a->theta,
@@ -808,9 +825,15 @@ extern "C" int pf_migrate_pack(pf_handle* h, const pf_agents* a, uint32_t* up_bu
 
 extern "C" int pf_migrate_unpack(pf_handle* h, const pf_agents* a, const uint32_t* buf, int64_t cap,
                                  void* stream) {
+  return pf_migrate_unpack2(h, a, buf, nullptr, cap, stream);
+}
+
+extern "C" int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32_t* buf, const uint32_t* buf2,
+                                  int64_t cap, void* stream) {
   int rc = check_agents(h, a);
   if (rc) return rc;
-  if (!buf || cap < 0) return PF_EINVAL;
+  if ((!buf && !buf2) || cap < 0) return PF_EINVAL;
+  h->mig_flags_n = 0;
   if (a->n == 0) return PF_OK;
   rc = pf_reserve_agents(h, a->n);
   if (rc) return rc;
@@ -822,7 +845,7 @@ extern "C" int pf_migrate_unpack(pf_handle* h, const pf_agents* a, const uint32_
   PF_LAUNCH_CHECK(h);
   size_t bytes = h->cub_temp_bytes;
   PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
-  k_migrate_fill<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, flags, ranks, buf, cap, a->x, a->y, a->theta,
+  k_migrate_fill<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, flags, ranks, buf, buf2, cap, a->x, a->y, a->theta,
                                                       a->wl, a->wr, a->meta, a->gid, h->counters);
   PF_LAUNCH_CHECK(h);
   return PF_OK;

@@ -243,8 +243,11 @@ class PheroField:
         self._ck(self._L.pf_migrate_pack(self._h, C.byref(a.struct()), _ptr(up), _ptr(down), cap,
                                          self._s()))
 
-    def migrate_unpack(self, a: Swarm, buf: torch.Tensor, cap: int):
-        self._ck(self._L.pf_migrate_unpack(self._h, C.byref(a.struct()), _ptr(buf), cap, self._s()))
+    def migrate_unpack(self, a: Swarm, buf: Optional[torch.Tensor], cap: int,
+                       buf2: Optional[torch.Tensor] = None):
+        """place the records of `buf`, then of `buf2`, into the lowest empty slots (one pass)"""
+        self._ck(self._L.pf_migrate_unpack2(self._h, C.byref(a.struct()), _ptr(buf), _ptr(buf2), cap,
+                                            self._s()))
 
     # -- counters / tuning
     def counters(self) -> abi.PFCounters:

@@ -113,10 +113,10 @@ class CudaStrip:
         self.field.migrate_pack(self.swarm, self.send_up, self.send_down, self.mcap)
 
     def unpack(self, from_up: bool, from_down: bool):
-        if from_up:
-            self.field.migrate_unpack(self.swarm, self.recv_up, self.mcap)
-        if from_down:
-            self.field.migrate_unpack(self.swarm, self.recv_down, self.mcap)
+        # one pass: arrivals from the upper neighbour first, then from the lower one
+        if from_up or from_down:
+            self.field.migrate_unpack(self.swarm, self.recv_up if from_up else None, self.mcap,
+                                      self.recv_down if from_down else None)
 
     def synchronize(self):
         torch.cuda.synchronize(self.field.device)
@@ -159,16 +159,31 @@ class StripWorker:
             out.append((self.rank + 1, bottom))
         return out
 
-    def field_interior(self):
-        if self.b.rows > 2:
-            self.b.field_rows(1, self.b.rows - 1)
-
-    def field_edges_and_agents(self, sense_enabled: bool, move: bool = True):
+    # phase 3: the stencil is split so that both exchanges hide behind it —
+    #   interior part A  (while the halo is in flight)
+    #   agents           (needs the ghost rows; produces the leavers)
+    #   interior part B + the two edge rows (while the migration buffers are in flight)
+    def _split(self):
         rows = self.b.rows
+        lo, hi = 1, max(1, rows - 1)
+        return lo, lo + (hi - lo) // 2, hi
+
+    def field_interior_a(self):
+        lo, mid, _ = self._split()
+        if mid > lo:
+            self.b.field_rows(lo, mid)
+
+    def agents(self, sense_enabled: bool, move: bool = True):
+        self.b.agents(self.flags(sense_enabled, move))
+
+    def field_rest(self):
+        rows = self.b.rows
+        _, mid, hi = self._split()
+        if hi > mid:
+            self.b.field_rows(mid, hi)
         self.b.field_rows(0, min(1, rows))
         if rows > 1:
             self.b.field_rows(rows - 1, rows)
-        self.b.agents(self.flags(sense_enabled, move))
         self.b.swap()
 
     # phase 4
@@ -220,12 +235,12 @@ class LocalDriver:
             w.deposit(sense_enabled)
         self._move(self.w, lambda w: w.halo_sends(), lambda w: w.halo_recvs())
         for w in self.w:
-            w.field_interior()
-            w.field_edges_and_agents(sense_enabled)
-        for w in self.w:
+            w.field_interior_a()
+            w.agents(sense_enabled)
             w.pack()
         self._move(self.w, lambda w: w.migrate_sends(), lambda w: w.migrate_recvs())
         for w in self.w:
+            w.field_rest()
             w.unpack()
 
 
@@ -246,6 +261,8 @@ class DistDriver:
             self.comm_stream = torch.cuda.Stream()
             self.ev_ready = torch.cuda.Event()
             self.ev_done = torch.cuda.Event()
+            self.ev_pack = torch.cuda.Event()
+            self.ev_mig = torch.cuda.Event()
 
     def _exchange(self, sends, recvs):
         dist = self.dist
@@ -260,33 +277,49 @@ class DistDriver:
             return []
         return dist.batch_isend_irecv(ops)
 
+    def _comm(self, sends, recvs, ev_before, ev_after):
+        """run one neighbour exchange on the comm stream, fenced by events against the main stream"""
+        main = torch.cuda.current_stream()
+        ev_before.record(main)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev_before)
+            for r in self._exchange(sends, recvs):
+                r.wait()
+            ev_after.record(self.comm_stream)
+
     def tick(self, sense_enabled: bool = True, move: bool = True):
         """move=False: the caller owns the poses (pf_agents_observe); nothing migrates"""
         w = self.w
         w.deposit(sense_enabled)
         if self.overlap:
             main = torch.cuda.current_stream()
-            self.ev_ready.record(main)
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(self.ev_ready)
-                reqs = self._exchange(w.halo_sends(), w.halo_recvs())
-                for r in reqs:
-                    r.wait()
-                self.ev_done.record(self.comm_stream)
-            w.field_interior()
+            self._comm(w.halo_sends(), w.halo_recvs(), self.ev_ready, self.ev_done)
+            w.field_interior_a()                 # overlaps the halo
             main.wait_event(self.ev_done)
-        else:
-            for r in self._exchange(w.halo_sends(), w.halo_recvs()):
-                r.wait()
-            w.field_interior()
-        w.field_edges_and_agents(sense_enabled, move)
-        if not move:
-            w.ticks += 1
+            w.agents(sense_enabled, move)
+            if move:
+                w.pack()
+                self._comm(w.migrate_sends(), w.migrate_recvs(), self.ev_pack, self.ev_mig)
+            w.field_rest()                       # overlaps the migration exchange
+            if move:
+                main.wait_event(self.ev_mig)
+                w.unpack()
+            else:
+                w.ticks += 1
             return
-        w.pack()
-        for r in self._exchange(w.migrate_sends(), w.migrate_recvs()):
+        for r in self._exchange(w.halo_sends(), w.halo_recvs()):
             r.wait()
-        w.unpack()
+        w.field_interior_a()
+        w.agents(sense_enabled, move)
+        if move:
+            w.pack()
+            for r in self._exchange(w.migrate_sends(), w.migrate_recvs()):
+                r.wait()
+        w.field_rest()
+        if move:
+            w.unpack()
+        else:
+            w.ticks += 1
 
 
 def partition_agents(cfg: abi.PFConfig, world: int, x, y, theta, state=None, gid=None):

@@ -77,6 +77,7 @@ class OracleStrip:
 
     def unpack(self, from_up, from_down):
         a = self.a
+        # arrivals from the upper neighbour first, then from the lower one, lowest empty slot first
         for use, buf in ((from_up, self.recv_up), (from_down, self.recv_down)):
             if not use:
                 continue
