@@ -308,6 +308,7 @@ int pf_profile_read(pf_handle* h, pf_profile* out_host, int reset);
 
 /* tuning options */
 #define PF_OPT_OVERLAP_AGENTS 1 /* pf_step: run sense/decide/move on a side stream beside the stencil */
+#define PF_OPT_NO_FUSED_KEYS 2  /* pf_step: always build deposit keys in their own kernel */
 int pf_set_option(pf_handle* h, int option, int value);
 
 /* which stencil kernel variant pf_step_field uses: 0 = auto, 1 = register sliding window (LDG),

@@ -213,9 +213,10 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
               float* __restrict__ ax, float* __restrict__ ay, float* __restrict__ ath,
               float* __restrict__ awl, float* __restrict__ awr, uint32_t* __restrict__ ameta,
               uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters,
-              unsigned long long* __restrict__ mig_flags) {
-  __shared__ unsigned int hist[8];
-  if (threadIdx.x < 8) hist[threadIdx.x] = 0;
+              unsigned long long* __restrict__ mig_flags, uint32_t* __restrict__ next_keys,
+              float* __restrict__ next_vals, uint32_t sentinel) {
+  __shared__ unsigned int hist[9];  // 0..5 decisions, 6 grabbed, 7 delivered, 8 deposits (next tick)
+  if (threadIdx.x < 9) hist[threadIdx.x] = 0;
   __syncthreads();
   // grid-stride over a fixed grid: the decision histogram is flushed once per CTA
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -225,6 +226,7 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
     if (st == PF_STATE_EMPTY) {
       if (dec_out) dec_out[i] = PF_DEC_NONE;
       if (mig_flags) mig_flags[i] = 0ull;
+      if (next_keys) { next_keys[i] = sentinel; next_vals[i] = 0.0f; }
     } else {
       float x = ax[i], y = ay[i], th = ath[i], wl = awl[i], wr = awr[i];
       int dec = PF_DEC_NONE;
@@ -355,8 +357,28 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
       ath[i] = th;
       awl[i] = wl;
       awr[i] = wr;
-      ameta[i] = (mt & ~(PF_META_STATE_MASK | PF_META_MOVED | PF_META_DEC_MASK | PF_META_CARRY)) |
-                 st | moved | ((uint32_t)dec << PF_META_DEC_SHIFT) | carry;
+      uint32_t nm = (mt & ~(PF_META_STATE_MASK | PF_META_MOVED | PF_META_DEC_MASK | PF_META_CARRY)) |
+                    st | moved | ((uint32_t)dec << PF_META_DEC_SHIFT) | carry;
+      if (next_keys) {
+        // the next tick's deposit rule, evaluated here on the state it would read (identical to
+        // k_deposit_keys_agents; pf_step only asks for it when that deposit is certain to run)
+        uint32_t key = sentinel;
+        float amt = 0.0f;
+        if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && moved) {
+          uint32_t cnt = (nm >> PF_META_COUNT_SHIFT) + 1u;
+          amt = (st == PF_STATE_SEARCHING) ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
+                                           : p.i_homing;
+          nm = (nm & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
+          int r, q;
+          bool inside = pf_cell(p, x, y, r, q);
+          if (inside && r >= p.row0 && r < p.row1)
+            key = (uint32_t)(((long long)p.dep_ch[st] * p.rows + (r - p.row0)) * p.W + q);
+          atomicAdd(&hist[8], 1u);
+        }
+        next_keys[i] = key;
+        next_vals[i] = amt;
+      }
+      ameta[i] = nm;
       if (dec_out) dec_out[i] = (uint8_t)dec;
       if (mig_flags) {  // same rule as k_migrate_flags: did the (new) cell row leave the strip?
         int r, q;
@@ -368,6 +390,7 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
   __syncthreads();
   if (threadIdx.x < 8 && hist[threadIdx.x])
     atomicAdd(&counters[2 + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+  if (threadIdx.x == 8 && hist[8]) atomicAdd(&counters[1], (unsigned long long)hist[8]);
 }
 
 // storingPosition + has_moved (reference sup:279-289, 260-273) for externally measured poses

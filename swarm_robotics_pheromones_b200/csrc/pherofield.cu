@@ -43,6 +43,7 @@ struct pf_handle {
   uint64_t ticks;
   int variant, rows_per_cta;
   int overlap_agents;
+  int no_fused_keys;
   int n_sm, wave_keys, wave_agents;
   long long mig_flags_n;   // > 0: scratch holds the migration flags the last move kernel wrote
   const float* mig_flags_x;
@@ -254,7 +255,11 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
   CREATE_CUDA(cudaMalloc(&h->counters, sizeof(unsigned long long) * 16));
   CREATE_CUDA(cudaMemset(h->counters, 0, sizeof(unsigned long long) * 16));
   CREATE_CUDA(cudaMalloc(&h->d_sum, sizeof(double)));
-  CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // the side stream outranks the caller's: its small kernels are not starved
+    CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+  }
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   {
@@ -494,6 +499,7 @@ extern "C" int pf_swap(pf_handle* h) {
 extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (!h) return PF_EINVAL;
   if (option == PF_OPT_OVERLAP_AGENTS) { h->overlap_agents = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_NO_FUSED_KEYS) { h->no_fused_keys = value ? 1 : 0; return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
 }
 
@@ -578,7 +584,8 @@ extern "C" int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y,
   return PF_OK;
 }
 
-static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s) {
+static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s,
+                              bool emit_next_keys = false) {
   // on a strip, the move kernel also emits the leave-up / leave-down flags pf_migrate_pack needs
   unsigned long long* mig = nullptr;
   if (is_sharded(h) && (flags & PF_STEP_MOVE) && h->scratch && a->n <= h->cap) {
@@ -586,8 +593,15 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
     h->mig_flags_n = a->n;
     h->mig_flags_x = a->x;
   }
+  uint32_t* nk = nullptr;
+  float* nv = nullptr;
+  if (emit_next_keys && !mig) {  // keys_in / vals_in of the sort scratch, for the next tick's deposit
+    nk = (uint32_t*)h->scratch;
+    nv = (float*)(nk + 2 * h->cap);
+  }
   k_agents_step<<<wave_grid(a->n, h->wave_agents), 256, 0, s>>>(h->dev, h->buf[h->cur], flags, a->n, a->x, a->y,
-                                                     a->theta, a->wl, a->wr, a->meta, dec, h->counters, mig);
+                                                     a->theta, a->wl, a->wr, a->meta, dec, h->counters, mig,
+                                                     nk, nv, h->sentinel);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -690,6 +704,7 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
   if (rc) return rc;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
+  bool keys_ready = false;
   for (int t = 0; t < nsteps; ++t) {
     const double now = h->t0 + (double)h->ticks * (double)h->cfg.dt;
     const bool sense = (now >= h->start_delay) && (mask & PF_STEP_SENSE);
@@ -702,9 +717,11 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
       PF_CUDA(h, cudaEventRecord(pe[0], s));
     }
     if (now >= h->start_delay && (mask & PF_STEP_DEPOSIT) && a->n > 0) {  // deposit_pheromone, sup:577
-      rc = pf_agents_deposit(h, a, stream);
+      if (keys_ready) rc = sort_and_sum(h, a->n, s);  // keys came from the previous tick's move kernel
+      else rc = pf_agents_deposit(h, a, stream);
       if (rc) return rc;
     }
+    keys_ready = false;
     if (pe) PF_CUDA(h, cudaEventRecord(pe[1], s));
     // sense/decide/move (side stream) and evaporate+diffuse (main stream) both read the
     // post-deposit field and write disjoint data: run them concurrently
@@ -720,8 +737,13 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
         PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
       }
       if (pe) PF_CUDA(h, cudaEventRecord(pe[3], as));
-      rc = launch_agents_step(h, a, flags, nullptr, as);
+      // fuse the next tick's key generation into this tick's move kernel when that deposit is certain
+      const double next = h->t0 + (double)(h->ticks + 1) * (double)h->cfg.dt;
+      const bool emit = !h->no_fused_keys && (t + 1 < nsteps) && (mask & PF_STEP_DEPOSIT) &&
+                        next >= h->start_delay && !is_sharded(h);
+      rc = launch_agents_step(h, a, flags, nullptr, as, emit);
       if (rc) return rc;
+      keys_ready = emit;
       if (pe) PF_CUDA(h, cudaEventRecord(pe[4], as));
       if (fork) PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
     }
