@@ -306,6 +306,57 @@ typedef struct pf_profile {
 int pf_profile_enable(pf_handle* h, int on);
 int pf_profile_read(pf_handle* h, pf_profile* out_host, int reset);
 
+/* -------------------------------------------------------------------------------------------
+ * sparse timestamped trail: the shipped supervisor's per-robot trail dict for
+ * N robots, fp64, one thread per robot. Discrete outputs (deposit amounts, counts, sense lists,
+ * arg-max direction, decision) are exact; real-valued ones agree with CPython/glibc to ~1e-15.
+ * Replaces PheromoneAlgorithm's dict state + deposit/sense/adjust/evaporate and the tick drivers
+ * Controller.startPheromone / homing (sup:237-250, 291-525, 565-663).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pf_trail pf_trail;
+typedef struct pf_trail_out { /* device arrays of n_robots entries each; any may be NULL */
+  double* amount;       /* deposited intensity, NaN = "nothing deposited" (sup:321-322) */
+  int32_t* n_global;    /* len(global_pheromone_grid[name]) */
+  int8_t* direction;    /* arg-max PF_DIR_* of sup:440-450, -1 if the robot did not sense */
+  int8_t* decision;     /* PF_DEC_* */
+  double* wl;           /* adjusted_left_speed  */
+  double* wr;           /* adjusted_right_speed */
+  int32_t* n_live;      /* len(pheromone_grids[name]) after this tick's evaporation */
+  double* sum_live;     /* sum of live intensities after evaporation */
+  uint64_t* masks;      /* [5][n]: bit j set = live entry j (insertion order, before this tick's
+                           evaporation) is in the sensed list of direction PF_DIR_* */
+  double* pre_time;     /* [capacity][n]: times of the live entries as the sense step saw them */
+  double* pre_intensity;/* [capacity][n]: their intensities (before this tick's evaporation) */
+  int32_t* n_pre;       /* number of such entries */
+} pf_trail_out;
+int pf_trail_create(int device, int64_t n_robots, int capacity /* live entries per robot, <= 64 */,
+                    pf_trail** out);
+int pf_trail_destroy(pf_trail* t);
+const char* pf_trail_last_error(const pf_trail* t);
+/* start_host [n][3] (start_position, sup:248), food_host [3] (sup:419-422), state_host [n] or NULL */
+int pf_trail_configure(pf_trail* t, const double* start_host, const double* food_host,
+                       const uint8_t* state_host);
+int pf_trail_set_state(pf_trail* t, int64_t robot, int state);
+/* one supervisor tick for every robot: pos_xyz [n][3] and ps [n][8] are device fp64 arrays */
+int pf_trail_tick(pf_trail* t, double t_now, double start_delay, const double* pos_xyz,
+                  const double* ps, const pf_trail_out* out, void* stream);
+int pf_trail_entries(pf_trail* t, double** time, double** intensity, double** x, double** y,
+                     double** z, int** n_live, int* capacity);
+
+/* -------------------------------------------------------------------------------------------
+ * offline heat-map: graph.py:17-24 — per trajectory point `heatmap[|int(y*H)|,
+ * |int(x*W)|] += 20` followed by scipy.ndimage.gaussian_filter(heatmap, sigma) (mode 'reflect',
+ * truncate 4.0), fp64. weights_host = the normalised 1-D kernel's centre and right half
+ * (radius + 1 values), computed on the host the way scipy's _gaussian_kernel1d does.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pf_heatmap pf_heatmap;
+int pf_heatmap_create(int device, int H, int W, int radius, const double* weights_host, pf_heatmap** out);
+int pf_heatmap_destroy(pf_heatmap* h);
+const char* pf_heatmap_last_error(const pf_heatmap* h);
+int pf_heatmap_accumulate(pf_heatmap* h, int64_t n, const double* x_host, const double* y_host,
+                          double amount, void* stream);
+int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
+
 /* tuning options */
 #define PF_OPT_OVERLAP_AGENTS 1 /* pf_step: run sense/decide/move on a side stream beside the stencil */
 #define PF_OPT_NO_FUSED_KEYS 2  /* pf_step: always build deposit keys in their own kernel */

@@ -51,6 +51,18 @@ SIGNATURES = {
     "pf_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "pf_profile_enable": (C.c_int, [_vp, C.c_int]),
     "pf_profile_read": (C.c_int, [_vp, C.POINTER(abi.PFProfile), C.c_int]),
+    "pf_trail_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.POINTER(_vp)]),
+    "pf_trail_destroy": (C.c_int, [_vp]),
+    "pf_trail_last_error": (C.c_char_p, [_vp]),
+    "pf_trail_configure": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "pf_trail_set_state": (C.c_int, [_vp, C.c_int64, C.c_int]),
+    "pf_trail_tick": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, C.POINTER(abi.PFTrailOut), _vp]),
+    "pf_trail_entries": (C.c_int, [_vp] + [C.POINTER(_vp)] * 6 + [C.POINTER(C.c_int)]),
+    "pf_heatmap_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "pf_heatmap_destroy": (C.c_int, [_vp]),
+    "pf_heatmap_last_error": (C.c_char_p, [_vp]),
+    "pf_heatmap_accumulate": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_double, _vp]),
+    "pf_heatmap_snapshot_host": (C.c_int, [_vp, _vp, _vp]),
     "pf_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "pf_set_stencil_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
 }

@@ -130,6 +130,13 @@ class PFCounters(C.Structure):
     ]
 
 
+class PFTrailOut(C.Structure):
+    _fields_ = [("amount", C.c_void_p), ("n_global", C.c_void_p), ("direction", C.c_void_p),
+                ("decision", C.c_void_p), ("wl", C.c_void_p), ("wr", C.c_void_p),
+                ("n_live", C.c_void_p), ("sum_live", C.c_void_p), ("masks", C.c_void_p),
+                ("pre_time", C.c_void_p), ("pre_intensity", C.c_void_p), ("n_pre", C.c_void_p)]
+
+
 class PFProfile(C.Structure):
     _fields_ = [("ticks", C.c_uint64), ("deposit_ms", C.c_double), ("stencil_ms", C.c_double),
                 ("agents_ms", C.c_double)]

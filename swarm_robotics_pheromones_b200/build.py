@@ -34,7 +34,7 @@ def nvcc() -> str:
 
 
 def sources():
-    return [CSRC / "pherofield.cu"]
+    return [CSRC / "pherofield.cu", CSRC / "pf_trail.cu", CSRC / "pf_heatmap.cu"]
 
 
 def deps():
@@ -56,7 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     proc = subprocess.run(cmd, capture_output=True, text=True)
     (LIB_DIR / "build.log").write_text(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
+        errs = [ln for ln in (proc.stdout + proc.stderr).splitlines() if "error" in ln.lower()]
+        sys.stderr.write("\n".join(errs[:40]) + f"\n(full log: {LIB_DIR / 'build.log'})\n")
         raise RuntimeError("nvcc failed building libpherofield.so")
     if verbose:
         print(proc.stderr)

@@ -10,7 +10,7 @@
 // Deposit rule of deposit_pheromone (reference sup:291-358): gate on has_moved (sup:308-310),
 // SEARCHING: counter+1, every `high_every`-th deposit is 20.0 else 1.0 (sup:312-318);
 // HOMING: 5.0 (sup:346-348). The counter lives in meta bits 8..31.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
                       const float* __restrict__ y, uint32_t* __restrict__ meta,
                       uint32_t* __restrict__ keys, float* __restrict__ vals, uint32_t sentinel,
