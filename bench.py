@@ -235,6 +235,77 @@ def init_agents_torch(cfg, n, device, seed=1234):
     return x.float().numpy(), y.float().numpy(), th.float().numpy()
 
 
+def measure_other_config(name, steps, sort_every=32):
+    """short device-resident run of another BASELINE config (reported next to the headline)"""
+    import torch
+
+    from swarm_robotics_pheromones_b200.field import PheroField, Swarm
+    cfg, n = make_config(name)
+    x, y, th = init_agents_torch(cfg, n, "cuda")
+    f = PheroField(cfg)
+    sw = Swarm(x, y, th)
+    f.reserve_agents(n)
+    f.sort_agents(sw)
+    f.step(sw, 5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    done = 0
+    while done < steps:
+        m = min(sort_every, steps - done)
+        f.sort_agents(sw)
+        f.step(sw, m)
+        done += m
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    cells = cfg.H * cfg.W * cfg.C
+    c = f.counters()
+    out = {"workload": f"{name}: {cfg.H}x{cfg.W}x{cfg.C}, {n} agents, {cfg.stencil}-point",
+           "steps": steps, "ms_per_step": ms, "cell_updates_per_s": cells / (ms * 1e-3),
+           "agent_steps_per_s": n / (ms * 1e-3),
+           "whole_tick_GBs": (cells * 8 + n * 76 + 8 * min(n, cells)) / (ms * 1e-3) / 1e9}
+    if cfg.fsm:
+        out["food_grabbed"], out["food_delivered"] = int(c.food_grabbed), int(c.food_delivered)
+    f.close()
+    return out
+
+
+def measure_trail_engine(n_robots=1 << 20, ticks=50):
+    """sparse timestamped-trail engine (the shipped supervisor's data structure), robots x ticks / s"""
+    import torch
+
+    from swarm_robotics_pheromones_b200.trail import TrailSwarm
+    names = [str(i) for i in range(n_robots)]
+    rng = np.random.default_rng(0)
+    start = rng.uniform(-0.5, 0.5, (n_robots, 3))
+    start[:, 2] = 0.0
+    sw = TrailSwarm(names, start, [0.36, -0.15, 0.05], ps=60.0, start_delay=5.0, record_sense=False)
+    pos = torch.from_numpy(start).cuda()
+    step = torch.from_numpy(rng.normal(0, 0.003, (n_robots, 3)) * np.array([1, 1, 0])).cuda()
+    t = 5.0
+    for _ in range(40):  # fill the trails to steady state (about 44 live entries)
+        pos += step
+        sw.tick_device(t, pos)
+        t += 0.064
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(ticks):
+        pos += step
+        sw.tick_device(t, pos)
+        t += 0.064
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / ticks
+    live = float(sw.out["n_live"].float().mean().item())
+    sw.close()
+    return {"robots": n_robots, "ms_per_tick": ms, "robot_ticks_per_s": n_robots / (ms * 1e-3),
+            "mean_live_entries": live,
+            "reference_python_robot_ticks_per_s": 850.0,
+            "note": "reference figure: SURVEY §6, headless, 1 core, this container"}
+
+
 def run_single(args):
     import torch
 
@@ -277,8 +348,12 @@ def run_single(args):
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     l0 = field.launch_count()
-    field.profile(True)
-    field.profile_read(reset=True)
+    # launch-bound (small) problems replay ticks from a CUDA graph, which per-phase event profiling
+    # would disable: time them unprofiled and take the phase split from a second, profiled pass
+    small = cells <= (1 << 24)
+    if not small:
+        field.profile(True)
+        field.profile_read(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     torch.cuda.synchronize()
@@ -291,9 +366,14 @@ def run_single(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     sorts_timed = state["sorts"] - sorts0
+    launches = field.launch_count() - l0
+    if small:
+        field.profile(True)
+        field.profile_read(reset=True)
+        run_ticks(min(args.steps, 64))
+        torch.cuda.synchronize()
     prof = field.profile_read(reset=True)
     field.profile(False)
-    launches = field.launch_count() - l0
     ms_per_step = ms / args.steps
     value = cells * args.steps / (ms * 1e-3)
     agent_rate = n * args.steps / (ms * 1e-3)
@@ -340,6 +420,21 @@ def run_single(args):
            "steps": e2e_steps, "h2d_bytes_per_step": rc.h2d_bytes, "d2h_bytes_per_step": rc.d2h_bytes,
            "call": "ReferenceCompat.tick_host(pinned poses [3][N]) -> (wl, wr, decision) on host"}
 
+    # ---- the other BASELINE configs and the sparse-trail engine, short runs (context, not the headline)
+    others = None
+    trail_eng = None
+    if args.config == "c3" and not args.no_others and not args.grid:
+        others = {}
+        for name, k in (("c1", 2000), ("c2", 256), ("c4", 64)):
+            try:
+                others[name] = measure_other_config(name, k)
+            except Exception as e:  # never lose the headline over a side measurement
+                others[name] = {"error": repr(e)}
+        try:
+            trail_eng = measure_trail_engine()
+        except Exception as e:
+            trail_eng = {"error": repr(e)}
+
     # ---- CPU baseline (rank 0, N = 1): the oracle port on this box's host cores
     cb = None
     if not args.no_cpu:
@@ -354,6 +449,7 @@ def run_single(args):
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
         "stencil_variant": args.variant, "agent_sort_every": args.sort_every,
         "agent_sorts_in_timed_region": sorts_timed,
+        "other_configs": others, "sparse_trail_engine": trail_eng,
     }
     print(json.dumps(line), flush=True)
     field.close()
@@ -517,6 +613,7 @@ def main():
                     help="re-order the agent arrays by cell every this many ticks (0 = never)")
     ap.add_argument("--overlap-agents", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the c1/c2/c4 and trail side runs")
     ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -21,6 +21,13 @@
 
 static char g_create_err[512] = "";
 
+struct GraphKey {
+  const void *x, *y, *theta, *wl, *wr, *meta, *scratch;
+  long long n, cap;
+  uint32_t mask;
+  int parity, variant, rpc;
+};
+
 struct pf_handle {
   pf_config cfg;
   PFDev dev;
@@ -44,6 +51,11 @@ struct pf_handle {
   int variant, rows_per_cta;
   int overlap_agents;
   int no_fused_keys;
+  int use_graph;
+  cudaGraph_t g_graph;
+  cudaGraphExec_t g_exec;
+  GraphKey g_key;
+  uint64_t g_nodes;
   int n_sm, wave_keys, wave_agents;
   long long mig_flags_n;   // > 0: scratch holds the migration flags the last move kernel wrote
   const float* mig_flags_x;
@@ -86,6 +98,7 @@ static int set_err(pf_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 static bool is_sharded(const pf_handle* h) { return h->cfg.row0 > 0 || h->cfg.row1 < h->cfg.H; }
+static void graph_drop(pf_handle* h);
 
 static inline unsigned blocks_for(long long n, int threads) {
   return (unsigned)((n + threads - 1) / threads);
@@ -274,6 +287,8 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
 #undef CREATE_CUDA
   h->variant = 0;
   h->rows_per_cta = 0;
+  // launch-bound problems (field + agents small enough that a tick is a few tens of microseconds)
+  h->use_graph = (h->buf_elems <= (1ll << 24)) ? 1 : 0;
   tma_stencil_init(&h->tma);
   *out = h;
   return PF_OK;
@@ -292,6 +307,8 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
+  if (h->g_graph) cudaGraphDestroy(h->g_graph);
   if (h->prof_ev) {
     for (int i = 0; i < kProfSlots * 6; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;
@@ -500,6 +517,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (!h) return PF_EINVAL;
   if (option == PF_OPT_OVERLAP_AGENTS) { h->overlap_agents = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_FUSED_KEYS) { h->no_fused_keys = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
 }
 
@@ -695,6 +713,108 @@ extern "C" int pf_step(pf_handle* h, const pf_agents* a, int nsteps, void* strea
   return pf_step_ex(h, a, nsteps, PF_STEP_ALL, stream);
 }
 
+// One tick enqueued on `s`. keys_ready: the previous tick's move kernel already produced this tick's
+// deposit keys; emit_next: produce the next tick's keys in this tick's move kernel.
+static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream_t s, bool keys_ready,
+                     bool emit_next, bool* keys_ready_out) {
+  int rc;
+  const double now = h->t0 + (double)h->ticks * (double)h->cfg.dt;
+  const bool sense = (now >= h->start_delay) && (mask & PF_STEP_SENSE);
+  const uint32_t flags = (mask & PF_STEP_MOVE) | (sense ? PF_STEP_SENSE : 0u);
+  cudaEvent_t* pe = nullptr;
+  if (h->prof_on) {
+    if (h->prof_used == kProfSlots) { rc = prof_fold(h); if (rc) return rc; }
+    pe = h->prof_ev + 6 * h->prof_used;
+    h->prof_has_agents[h->prof_used] = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
+    PF_CUDA(h, cudaEventRecord(pe[0], s));
+  }
+  if (now >= h->start_delay && (mask & PF_STEP_DEPOSIT) && a->n > 0) {  // deposit_pheromone, sup:577
+    if (keys_ready) rc = sort_and_sum(h, a->n, s);  // keys came from the previous tick's move kernel
+    else rc = pf_agents_deposit(h, a, (void*)s);
+    if (rc) return rc;
+  }
+  *keys_ready_out = false;
+  if (pe) PF_CUDA(h, cudaEventRecord(pe[1], s));
+  const bool run_agents = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
+  // Measured on B200 (profiles/r01a_*): overlapped, the agent kernel is starved behind the
+  // stencil's CTAs and the pair takes 4.55 ms against 0.63 + 2.65 ms back to back, so the
+  // default is back to back on the caller's stream; PF_OPT_OVERLAP_AGENTS restores the fork.
+  const bool fork = run_agents && h->overlap_agents;
+  cudaStream_t as = fork ? h->side : s;
+  if (run_agents) {
+    if (fork) {
+      PF_CUDA(h, cudaEventRecord(h->ev_fork, s));
+      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    }
+    if (pe) PF_CUDA(h, cudaEventRecord(pe[3], as));
+    // fuse the next tick's key generation into this tick's move kernel when that deposit is certain
+    const double next = h->t0 + (double)(h->ticks + 1) * (double)h->cfg.dt;
+    const bool emit = emit_next && !h->no_fused_keys && (mask & PF_STEP_DEPOSIT) && next >= h->start_delay &&
+                      !is_sharded(h);
+    rc = launch_agents_step(h, a, flags, nullptr, as, emit);
+    if (rc) return rc;
+    *keys_ready_out = emit;
+    if (pe) PF_CUDA(h, cudaEventRecord(pe[4], as));
+    if (fork) PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+  }
+  if (pe) PF_CUDA(h, cudaEventRecord(pe[5], s));
+  if (mask & PF_STEP_FIELD) {
+    rc = launch_stencil(h, 0, h->dev.rows, s);
+    if (rc) return rc;
+  }
+  if (pe) {
+    PF_CUDA(h, cudaEventRecord(pe[2], s));
+    h->prof_used++;
+  }
+  if (fork) PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+  k_tick_counter<<<1, 1, 0, s>>>(h->counters);
+  PF_LAUNCH_CHECK(h);
+  if (mask & PF_STEP_FIELD) h->cur ^= 1;
+  h->ticks++;
+  return PF_OK;
+}
+
+static void graph_drop(pf_handle* h) {
+  if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
+  if (h->g_graph) cudaGraphDestroy(h->g_graph);
+  h->g_exec = nullptr;
+  h->g_graph = nullptr;
+}
+
+// Capture two steady-state ticks (the double buffer returns to its parity) into a CUDA graph.
+static int graph_prepare(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream_t s) {
+  GraphKey k;
+  memset(&k, 0, sizeof(k));
+  k.x = a->x; k.y = a->y; k.theta = a->theta; k.wl = a->wl; k.wr = a->wr; k.meta = a->meta;
+  k.n = a->n; k.mask = mask; k.parity = h->cur; k.variant = h->variant; k.rpc = h->rows_per_cta;
+  k.scratch = h->scratch; k.cap = h->cap;
+  if (h->g_exec && memcmp(&k, &h->g_key, sizeof(k)) == 0) return PF_OK;
+  graph_drop(h);
+  const uint64_t ticks0 = h->ticks, launches0 = h->launches;
+  // capture on the handle's own stream (the caller's may be the legacy default stream, which cannot
+  // be captured); the instantiated graph is then launched into the caller's stream
+  (void)s;
+  cudaStream_t cs = h->side;
+  PF_CUDA(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  bool kr = true;
+  int rc = tick_once(h, a, mask, cs, true, true, &kr);
+  if (rc == PF_OK) rc = tick_once(h, a, mask, cs, kr, true, &kr);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(cs, &g);
+  h->g_nodes = h->launches - launches0;
+  h->ticks = ticks0;       // capturing enqueues nothing: undo the host-side bookkeeping
+  h->launches = launches0;  // (two buffer flips cancel)
+  if (rc != PF_OK || e != cudaSuccess || !g || !kr) {
+    if (g) cudaGraphDestroy(g);
+    if (rc == PF_OK) rc = set_err(h, PF_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    return rc;
+  }
+  h->g_graph = g;
+  PF_CUDA(h, cudaGraphInstantiate(&h->g_exec, g, 0));
+  h->g_key = k;
+  return PF_OK;
+}
+
 extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t mask, void* stream) {
   int rc = check_agents(h, a);
   if (rc) return rc;
@@ -705,62 +825,36 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   bool keys_ready = false;
-  for (int t = 0; t < nsteps; ++t) {
-    const double now = h->t0 + (double)h->ticks * (double)h->cfg.dt;
-    const bool sense = (now >= h->start_delay) && (mask & PF_STEP_SENSE);
-    const uint32_t flags = (mask & PF_STEP_MOVE) | (sense ? PF_STEP_SENSE : 0u);
-    cudaEvent_t* pe = nullptr;
-    if (h->prof_on) {
-      if (h->prof_used == kProfSlots) { rc = prof_fold(h); if (rc) return rc; }
-      pe = h->prof_ev + 6 * h->prof_used;
-      h->prof_has_agents[h->prof_used] = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
-      PF_CUDA(h, cudaEventRecord(pe[0], s));
-    }
-    if (now >= h->start_delay && (mask & PF_STEP_DEPOSIT) && a->n > 0) {  // deposit_pheromone, sup:577
-      if (keys_ready) rc = sort_and_sum(h, a->n, s);  // keys came from the previous tick's move kernel
-      else rc = pf_agents_deposit(h, a, stream);
-      if (rc) return rc;
-    }
-    keys_ready = false;
-    if (pe) PF_CUDA(h, cudaEventRecord(pe[1], s));
-    // sense/decide/move (side stream) and evaporate+diffuse (main stream) both read the
-    // post-deposit field and write disjoint data: run them concurrently
-    const bool run_agents = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
-    // Measured on B200 (profiles/r01a_*): overlapped, the agent kernel is starved behind the
-    // stencil's CTAs and the pair takes 4.55 ms against 0.63 + 2.65 ms back to back, so the
-    // default is back to back on the caller's stream; PF_OPT_OVERLAP_AGENTS restores the fork.
-    const bool fork = run_agents && h->overlap_agents;
-    cudaStream_t as = fork ? h->side : s;
-    if (run_agents) {
-      if (fork) {
-        PF_CUDA(h, cudaEventRecord(h->ev_fork, s));
-        PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  int t = 0;
+  // CUDA-graph path for launch-bound (small) problems: tick 0 normally (builds keys), then pairs of
+  // steady-state ticks replayed from one graph, the last tick normally (must not pre-bump the
+  // deposit counters for a tick that this call does not run).
+  const double now0 = h->t0 + (double)h->ticks * (double)h->cfg.dt;
+  const bool graph_ok = h->use_graph && !h->prof_on && !h->overlap_agents && !h->no_fused_keys && a->n > 0 &&
+                        nsteps >= 6 && mask == PF_STEP_ALL && now0 >= h->start_delay;
+  if (graph_ok) {
+    rc = tick_once(h, a, mask, s, false, true, &keys_ready);
+    if (rc) return rc;
+    t = 1;
+    if (keys_ready) {
+      const int pairs = (nsteps - 2) / 2;
+      rc = graph_prepare(h, a, mask, s);
+      if (rc == PF_OK) {
+        for (int p = 0; p < pairs; ++p) {
+          PF_CUDA(h, cudaGraphLaunch(h->g_exec, s));
+          h->ticks += 2;
+          h->launches += h->g_nodes;
+        }
+        t += 2 * pairs;
+      } else {
+        h->use_graph = 0;  // fall back to plain launches for good; the error text stays readable
+        cudaGetLastError();  // clear the pending error so the plain path starts clean
       }
-      if (pe) PF_CUDA(h, cudaEventRecord(pe[3], as));
-      // fuse the next tick's key generation into this tick's move kernel when that deposit is certain
-      const double next = h->t0 + (double)(h->ticks + 1) * (double)h->cfg.dt;
-      const bool emit = !h->no_fused_keys && (t + 1 < nsteps) && (mask & PF_STEP_DEPOSIT) &&
-                        next >= h->start_delay && !is_sharded(h);
-      rc = launch_agents_step(h, a, flags, nullptr, as, emit);
-      if (rc) return rc;
-      keys_ready = emit;
-      if (pe) PF_CUDA(h, cudaEventRecord(pe[4], as));
-      if (fork) PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
     }
-    if (pe) PF_CUDA(h, cudaEventRecord(pe[5], s));
-    if (mask & PF_STEP_FIELD) {
-      rc = launch_stencil(h, 0, h->dev.rows, s);
-      if (rc) return rc;
-    }
-    if (pe) {
-      PF_CUDA(h, cudaEventRecord(pe[2], s));
-      h->prof_used++;
-    }
-    if (fork) PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-    k_tick_counter<<<1, 1, 0, s>>>(h->counters);
-    PF_LAUNCH_CHECK(h);
-    if (mask & PF_STEP_FIELD) h->cur ^= 1;
-    h->ticks++;
+  }
+  for (; t < nsteps; ++t) {
+    rc = tick_once(h, a, mask, s, keys_ready, t + 1 < nsteps, &keys_ready);
+    if (rc) return rc;
   }
   return PF_OK;
 }

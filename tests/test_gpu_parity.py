@@ -439,3 +439,38 @@ def test_agents_sort_keeps_results_by_gid():
         assert (got["meta"][:n][order] == a_np.meta).all()
         assert_bitexact(g.snapshot(), o.field, "field after sorted ticks")
     g.close()
+
+
+def test_graph_replay_equals_plain_launches_and_oracle():
+    # small (launch-bound) problems replay pairs of ticks from a CUDA graph; odd/even tick counts,
+    # repeated calls (graph reuse) and an agent sort in between (graph re-capture not needed) must
+    # all give the oracle's result
+    cfg = make_cfg(512, 1024, 2, 5, D=0.08)
+    cfg.fsm = 1
+    rng = np.random.default_rng(123)
+    n = 3000
+    x, y, th, _ = rand_agents(rng, cfg, n, margin=0.05)
+    st = rng.integers(1, 3, n)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    g.set_option(abi.OPT_USE_GRAPH, 1)
+    sw = Swarm(x, y, th, st)
+    launches = []
+    for k in (7, 12, 6, 33, 1, 2, 9):
+        l0 = g.launch_count()
+        o.tick(a_np, k)
+        g.step(sw, k)
+        launches.append(g.launch_count() - l0)
+        _compare_agents(sw, a_np, f"after {k} ticks")
+        assert_bitexact(g.snapshot(), o.field, f"field after {k} ticks")
+    c = g.counters()
+    assert c.ticks == 70 and c.deposits == int(o.counters[8])
+    assert list(c.decisions) == [int(v) for v in o.counters[:6]]
+    # the same run without graphs gives the same state
+    g2 = PheroField(cfg)
+    g2.set_option(abi.OPT_USE_GRAPH, 0)
+    sw2 = Swarm(x, y, th, st)
+    g2.step(sw2, 70)
+    assert_bitexact(g2.snapshot(), g.snapshot())
+    g.close(); g2.close()
