@@ -406,18 +406,25 @@ def run_single(args):
     pose[1].copy_(torch.from_numpy(cur["y"]))
     pose[2].copy_(torch.from_numpy(cur["theta"]))
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        rc.tick_host(pose)
+    # the "physics" between ticks is not ours to time: two pre-made pinned pose sets 3 mm apart are
+    # fed alternately, so every robot has moved (>= 1.5 mm) and deposits on every tick
+    pose_b = torch.empty_like(pose).pin_memory()
+    pose_b.copy_(pose)
+    pose_b[0].add_(3e-3)
+    poses = (pose_b, pose)
+    for k in range(2):
+        rc.tick_host(poses[k % 2])
     torch.cuda.synchronize()
+    dep0 = field.counters().deposits
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        wl, wr, dec = rc.tick_host(pose)  # synchronous: the supervisor needs the speeds
-        pose[0].add_(1e-3)  # the "physics" moves the robots between ticks (host side)
+    for k in range(e2e_steps):
+        wl, wr, dec = rc.tick_host(poses[k % 2])  # synchronous: the supervisor needs the speeds
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e = {"value": cells * e2e_steps / e2e_s, "unit": "cell-updates/s",
            "agent_steps_per_s": n * e2e_steps / e2e_s, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "steps": e2e_steps, "h2d_bytes_per_step": rc.h2d_bytes, "d2h_bytes_per_step": rc.d2h_bytes,
+           "deposits_per_step": (field.counters().deposits - dep0) / e2e_steps,
            "call": "ReferenceCompat.tick_host(pinned poses [3][N]) -> (wl, wr, decision) on host"}
 
     # ---- the other BASELINE configs and the sparse-trail engine, short runs (context, not the headline)
@@ -535,17 +542,25 @@ def run_sharded(args):
     d_pose = torch.empty((3, nl), dtype=torch.float32, device="cuda")
     h_out = torch.empty((2, nl), dtype=torch.float32).pin_memory()
     d_out = torch.empty((2, nl), dtype=torch.float32, device="cuda")
-    h_dec = torch.empty(nl, dtype=torch.int32).pin_memory()
     h_pose[0].copy_(sw.x.cpu()); h_pose[1].copy_(sw.y.cpu()); h_pose[2].copy_(sw.theta.cpu())
+    h_pose_b = torch.empty_like(h_pose).pin_memory()
+    h_pose_b.copy_(h_pose)
+    h_pose_b[1].add_(3e-3)  # along y: no agent changes strip, every agent has moved
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    d_dec = torch.empty(nl, dtype=torch.uint8, device="cuda")
+    h_dec = torch.empty(nl, dtype=torch.uint8).pin_memory()
+    e2e_k = [0]
 
     def e2e_tick():
-        d_pose.copy_(h_pose, non_blocking=True)
+        src = h_pose_b if e2e_k[0] % 2 == 0 else h_pose
+        e2e_k[0] += 1
+        d_pose.copy_(src, non_blocking=True)
         strip.field.observe(sw, d_pose[0], d_pose[1], d_pose[2])
         drv.tick(True, move=False)
-        d_out[0].copy_(sw.wl); d_out[1].copy_(sw.wr)
-        h_out.copy_(d_out, non_blocking=True)
-        h_dec.copy_((sw.meta & abi.META_DEC_MASK) >> abi.META_DEC_SHIFT, non_blocking=True)
+        h_out[0].copy_(sw.wl, non_blocking=True)
+        h_out[1].copy_(sw.wr, non_blocking=True)
+        d_dec.copy_((sw.meta & abi.META_DEC_MASK) >> abi.META_DEC_SHIFT)
+        h_dec.copy_(d_dec, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     e2e_tick()
@@ -558,7 +573,7 @@ def run_sharded(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
-    bytes_io = torch.tensor([h_pose.numel() * 4, h_out.numel() * 4 + h_dec.numel() * 4], device="cuda",
+    bytes_io = torch.tensor([h_pose.numel() * 4, h_out.numel() * 4 + h_dec.numel()], device="cuda",
                             dtype=torch.float64)
     dist.all_reduce(bytes_io)
     counts = torch.tensor([float(sw.alive().sum().item())], device="cuda", dtype=torch.float64)

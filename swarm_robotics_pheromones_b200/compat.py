@@ -200,6 +200,7 @@ class ReferenceCompat:
         if not hasattr(self, "_side"):
             self._side = torch.cuda.Stream(f.device)
             self._ev_dep = torch.cuda.Event()
+            self._ev_dec = torch.cuda.Event()
             self._ev_out = torch.cuda.Event()
         t, _ = f.time()
         sensing = t >= f.start_delay
@@ -207,13 +208,14 @@ class ReferenceCompat:
         f.observe(sw, self._d_pose[0], self._d_pose[1], self._d_pose[2])
         if sensing:
             f.agents_deposit(sw)
-        self._ev_dep.record(main)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ev_dep)
-            f.agents_step(sw, abi.STEP_SENSE if sensing else 0)
+        # decide on the main stream (two HBM-bound kernels side by side only slow each other down);
+        # the kernel writes the u8 decisions itself
+        f.agents_step(sw, abi.STEP_SENSE if sensing else 0, decisions=self._d_dec)
+        self._ev_dec.record(main)
+        with torch.cuda.stream(self._side):  # D2H rides beside the stencil
+            self._side.wait_event(self._ev_dec)
             self._h_out[0].copy_(sw.wl, non_blocking=True)
             self._h_out[1].copy_(sw.wr, non_blocking=True)
-            self._d_dec.copy_((sw.meta & abi.META_DEC_MASK) >> abi.META_DEC_SHIFT)
             self._h_dec.copy_(self._d_dec, non_blocking=True)
             self._ev_out.record(self._side)
         f.step(sw, 1, abi.STEP_FIELD)  # evaporate+diffuse only; advances the tick clock
