@@ -488,7 +488,7 @@ def run_sharded(args):
     del x, y, th, rows
     strip.field.set_stencil_variant(args.variant, args.rows_per_cta)
     worker = sharded.StripWorker(strip, rank, world)
-    drv = sharded.DistDriver(worker, overlap=not args.no_overlap)
+    drv = sharded.DistDriver(worker, overlap=not args.no_overlap, profile=args.phase_profile)
     cells = cfg.H * cfg.W * cfg.C
 
     tick_no = [0]
@@ -603,6 +603,8 @@ def run_sharded(args):
             "halo_overlap": not args.no_overlap, "stencil_variant": args.variant,
             "agent_sort_every": args.sort_every,
         }
+        if args.phase_profile:
+            line["phase_ms_rank0"] = sharded.phase_means(drv)
         print(json.dumps(line), flush=True)
     dist.barrier()
     strip.field.close()
@@ -630,6 +632,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the c1/c2/c4 and trail side runs")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--phase-profile", action="store_true", help="sharded run: per-phase CUDA events")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps

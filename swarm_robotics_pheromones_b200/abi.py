@@ -33,6 +33,7 @@ META_COUNT_SHIFT = 8
 OPT_OVERLAP_AGENTS = 1
 OPT_NO_FUSED_KEYS = 2
 OPT_USE_GRAPH = 3
+OPT_NO_OWNER_DEPOSIT = 4
 STEP_DEPOSIT, STEP_SENSE, STEP_FIELD, STEP_MOVE, STEP_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 
 # reference constants --------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 // pf_agents.cuh — K2 (deterministic deposit) and K3 (sense -> decide -> move) kernels.
 #pragma once
 #include "pf_device.cuh"
+#include "pf_deposit_owner.cuh"
 
 // ------------------------------------------------------------------------------------------
 // K2a: sort keys. key = local linear cell index ((ch*rows + lr)*W + col); agents that do not
@@ -14,7 +15,8 @@ __global__ void __launch_bounds__(256, 8)
 k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
                       const float* __restrict__ y, uint32_t* __restrict__ meta,
                       uint32_t* __restrict__ keys, float* __restrict__ vals, uint32_t sentinel,
-                      unsigned long long* __restrict__ counters) {
+                      unsigned long long* __restrict__ counters, uint32_t* __restrict__ cmin,
+                      uint32_t* __restrict__ cmax) {
   // grid-stride over a fixed grid (a multiple of the SM count): the deposit counter costs one
   // global atomic per CTA instead of one per warp (same-address atomics serialise in L2)
   __shared__ unsigned int s_dep;
@@ -44,6 +46,10 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
     keys[i] = key;
     vals[i] = amt;
     ndep += dep ? 1u : 0u;
+    if (cmin) {
+      const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
+      owner_note_bounds(cmin, cmax, i / kOwnChunk, key % plane, key != sentinel);
+    }
   }
   ndep = __reduce_add_sync(0xffffffffu, ndep);
   if ((threadIdx.x & 31) == 0 && ndep) atomicAdd(&s_dep, ndep);
@@ -214,7 +220,8 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
               float* __restrict__ awl, float* __restrict__ awr, uint32_t* __restrict__ ameta,
               uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters,
               unsigned long long* __restrict__ mig_flags, uint32_t* __restrict__ next_keys,
-              float* __restrict__ next_vals, uint32_t sentinel) {
+              float* __restrict__ next_vals, uint32_t sentinel, uint32_t* __restrict__ cmin,
+              uint32_t* __restrict__ cmax) {
   __shared__ unsigned int hist[9];  // 0..5 decisions, 6 grabbed, 7 delivered, 8 deposits (next tick)
   if (threadIdx.x < 9) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -377,6 +384,10 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
         }
         next_keys[i] = key;
         next_vals[i] = amt;
+        if (cmin) {
+          const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
+          owner_note_bounds(cmin, cmax, i / kOwnChunk, key % plane, key != sentinel);
+        }
       }
       ameta[i] = nm;
       if (dec_out) dec_out[i] = (uint8_t)dec;

@@ -1,0 +1,259 @@
+// pf_deposit_owner.cuh — K2 variant "owner computes": deterministic deposit WITHOUT a global sort.
+//
+// After pf_agents_sort the agent arrays are ordered by cell, and agents move well under one cell per
+// tick, so the arrays stay nearly ordered for dozens of ticks. At sort time the sorted key sequence is
+// cut into splitters every kOwnChunk agents; CTA b owns the cells whose key lies in
+// [split[b], split[b+1]) — about kOwnChunk agents, whatever the local density. Every tick
+//   1. the key producer (move kernel or key kernel) also records, per array chunk of kOwnChunk
+//      agents, the min and max cell key it wrote (two atomics per warp);
+//   2. k_owner_bounds turns them into a prefix-max / suffix-min pair, so that "every chunk that can
+//      hold a key in [lo, hi)" is a contiguous, binary-searchable chunk range — a guaranteed
+//      superset, however far agents have drifted;
+//   3. k_deposit_owner: each CTA scans its candidate chunks (L2-resident re-reads), compacts the
+//      agents that fall into its key range in ARRAY ORDER, block-radix-sorts them by cell (stable),
+//      sums each cell's amounts in that order and adds the total to the field — one writer per cell,
+//      no atomics on the field, same summation order as the global-sort path and the oracle.
+//      Ranges holding more than kOwnCap agents are bisected (work stack); a single cell holding more
+//      than kOwnCap agents is summed sequentially.
+#pragma once
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+
+#include "pf_device.cuh"
+
+constexpr int kOwnChunk = 1024;
+constexpr int kOwnThreads = 256;
+constexpr int kOwnItems = 8;
+constexpr int kOwnCap = kOwnThreads * kOwnItems;  // 2048 agents per sort
+
+// record the per-chunk key bounds (called by every thread of a warp whose lanes cover consecutive
+// agents of ONE chunk; `sk` = sort key, or 0xffffffff when the agent does not deposit)
+__device__ __forceinline__ void owner_note_bounds(uint32_t* __restrict__ cmin, uint32_t* __restrict__ cmax,
+                                                  long long chunk, uint32_t sk, bool deposits) {
+  uint32_t lo = deposits ? sk : 0xffffffffu;
+  uint32_t hi = deposits ? sk : 0u;
+  unsigned act = __activemask();
+  lo = __reduce_min_sync(act, lo);
+  hi = __reduce_max_sync(act, hi);
+  if ((threadIdx.x & 31) == (__ffs(act) - 1) && lo != 0xffffffffu) {
+    atomicMin(&cmin[chunk], lo);
+    atomicMax(&cmax[chunk], hi);
+  }
+}
+
+// prefix max of cmax, suffix min of cmin; one CTA; also resets cmin/cmax for the next tick
+__global__ void __launch_bounds__(1024)
+k_owner_bounds(int nchunks, uint32_t* __restrict__ cmin, uint32_t* __restrict__ cmax,
+               uint32_t* __restrict__ pmax, uint32_t* __restrict__ smin) {
+  typedef cub::BlockScan<uint32_t, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0u;
+  __syncthreads();
+  for (int base = 0; base < nchunks; base += 1024) {
+    int j = base + threadIdx.x;
+    uint32_t v = j < nchunks ? cmax[j] : 0u, out;
+    Scan(tmp).InclusiveScan(v, out, cub::Max());
+    uint32_t c = carry;
+    out = max(out, c);
+    if (j < nchunks) pmax[j] = out;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = out;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) carry = 0xffffffffu;
+  __syncthreads();
+  for (int base = 0; base < nchunks; base += 1024) {  // reversed index
+    int j = nchunks - 1 - (base + threadIdx.x);
+    uint32_t v = j >= 0 ? cmin[j] : 0xffffffffu, out;
+    Scan(tmp).InclusiveScan(v, out, cub::Min());
+    uint32_t c = carry;
+    out = min(out, c);
+    if (j >= 0) smin[j] = out;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = out;
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < nchunks; j += 1024) {
+    cmin[j] = 0xffffffffu;
+    cmax[j] = 0u;
+  }
+}
+
+// splitters from the sorted keys of pf_agents_sort: split[b] = sorted_key[b * kOwnChunk] (offset into
+// the strip's local key space), split[0] = 0, split[nb] = plane
+__global__ void k_owner_splitters(const uint32_t* __restrict__ sorted_keys, long long n, int nb,
+                                  uint32_t key_offset, uint32_t plane, uint32_t* __restrict__ split) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  uint32_t v;
+  if (b == 0) v = 0u;
+  else if (b == nb) v = plane;
+  else {
+    uint32_t k = sorted_keys[(long long)b * kOwnChunk];
+    // empty slots sort last with a sentinel beyond every cell; keys above/below the strip clamp
+    v = (k < key_offset) ? 0u : (k - key_offset > plane ? plane : k - key_offset);
+  }
+  split[b] = v;
+}
+
+__global__ void __launch_bounds__(kOwnThreads)
+k_deposit_owner(PFDev p, long long n, int nchunks, const uint32_t* __restrict__ keys,
+                const float* __restrict__ vals, uint32_t sentinel, const uint32_t* __restrict__ split,
+                const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ smin,
+                float* __restrict__ field) {
+  typedef cub::BlockRadixSort<uint32_t, kOwnThreads, kOwnItems, uint32_t> Sort;
+  typedef cub::BlockScan<int, kOwnThreads> Scan;
+  __shared__ union {
+    typename Sort::TempStorage sort;
+    typename Scan::TempStorage scan;
+  } tmp;
+  __shared__ uint32_t lk[kOwnCap];  // local keys of the selected agents, array order / sorted order
+  __shared__ uint32_t lv[kOwnCap];  // their amounts (bit patterns)
+  __shared__ uint32_t st_lo[34], st_hi[34];
+  __shared__ int st_n;
+
+  const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
+  const int b = blockIdx.x;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    st_lo[0] = split[b];
+    st_hi[0] = split[b + 1];
+    st_n = (split[b] < split[b + 1]) ? 1 : 0;
+  }
+  __syncthreads();
+
+  while (true) {
+    __syncthreads();
+    if (st_n == 0) break;
+    const uint32_t lo = st_lo[st_n - 1], hi = st_hi[st_n - 1];
+    __syncthreads();
+    if (t == 0) st_n -= 1;
+    // candidate chunks: first j with pmax[j] >= lo ... last j with smin[j] < hi
+    int j0, j1;
+    {
+      int a = 0, z = nchunks;  // lower bound of pmax >= lo
+      while (a < z) { int m = (a + z) >> 1; if (pmax[m] >= lo) z = m; else a = m + 1; }
+      j0 = a;
+      a = 0; z = nchunks;      // first j with smin[j] >= hi  -> j1 = that - 1
+      while (a < z) { int m = (a + z) >> 1; if (smin[m] >= hi) z = m; else a = m + 1; }
+      j1 = a - 1;
+    }
+    __syncthreads();
+    const uint32_t span = hi - lo;
+    int count = 0;
+    for (int j = j0; j <= j1; ++j) {
+      const long long e0 = (long long)j * kOwnChunk + 4 * t;
+      uint32_t k4[4], v4[4];
+      int sel[4], nsel = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long e = e0 + q;
+        uint32_t key = sentinel;
+        if (e < n) key = keys[e];
+        k4[q] = key;
+        sel[q] = 0;
+        if (key != sentinel) {
+          const uint32_t ch = key / plane;
+          const uint32_t sk = key - ch * plane;
+          if (sk >= lo && sk < hi) {
+            sel[q] = 1;
+            k4[q] = ch * span + (sk - lo);
+            v4[q] = __float_as_uint(vals[e]);
+            ++nsel;
+          }
+        }
+      }
+      int off, total;
+      Scan(tmp.scan).ExclusiveSum(nsel, off, total);
+      __syncthreads();
+      if (count + total <= kOwnCap) {
+        int w = count + off;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (sel[q]) { lk[w] = k4[q]; lv[w] = v4[q]; ++w; }
+      }
+      count += total;
+    }
+    __syncthreads();
+
+    if (count == 0) continue;
+    if (count > kOwnCap) {
+      if (span > 1u) {  // bisect the key range; both halves are handled by this CTA
+        if (t == 0) {
+          const uint32_t mid = lo + span / 2u;
+          st_lo[st_n] = mid; st_hi[st_n] = hi; st_n += 1;
+          st_lo[st_n] = lo;  st_hi[st_n] = mid; st_n += 1;
+        }
+        continue;
+      }
+      // one cell holds more than kOwnCap agents: sum them sequentially, in array order
+      for (int ch = 0; ch < p.C; ++ch) {
+        float s = 0.0f;
+        bool any = false;
+        const uint32_t want = (uint32_t)ch * plane + lo;
+        for (int j = j0; j <= j1; ++j) {
+          const long long e0 = (long long)j * kOwnChunk + 4 * t;
+          int nsel = 0;
+          uint32_t v4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const long long e = e0 + q;
+            if (e < n && keys[e] == want) v4[nsel++] = __float_as_uint(vals[e]);
+          }
+          int off, total;
+          Scan(tmp.scan).ExclusiveSum(nsel, off, total);
+          __syncthreads();
+          for (int q = 0; q < nsel; ++q) lv[off + q] = v4[q];
+          __syncthreads();
+          if (t == 0)
+            for (int q = 0; q < total; ++q) {
+              float a = __uint_as_float(lv[q]);
+              s = any ? fadd(s, a) : a;
+              any = true;
+            }
+          __syncthreads();
+        }
+        if (t == 0 && any) {
+          const int lr = (int)(lo / (uint32_t)p.W), col = (int)(lo - (uint32_t)lr * (uint32_t)p.W);
+          float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
+          *cell = fadd(*cell, s);
+        }
+      }
+      continue;
+    }
+
+    // ---- stable block radix sort of the selected agents by cell, then ordered segmented sum
+    uint32_t sk8[kOwnItems], sv8[kOwnItems];
+#pragma unroll
+    for (int q = 0; q < kOwnItems; ++q) {
+      const int e = t * kOwnItems + q;
+      sk8[q] = e < count ? lk[e] : 0xffffffffu;
+      sv8[q] = e < count ? lv[e] : 0u;
+    }
+    __syncthreads();
+    unsigned long long maxkey = (unsigned long long)p.C * span;  // one past the largest local key
+    int end_bit = 1;
+    while ((1ull << end_bit) <= maxkey && end_bit < 32) ++end_bit;  // all-ones padding sorts last
+    Sort(tmp.sort).Sort(sk8, sv8, 0, end_bit);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kOwnItems; ++q) {
+      const int e = t * kOwnItems + q;
+      lk[e] = sk8[q];
+      lv[e] = sv8[q];
+    }
+    __syncthreads();
+    for (int e = t; e < count; e += kOwnThreads) {
+      const uint32_t key = lk[e];
+      if (e > 0 && lk[e - 1] == key) continue;  // not a segment head
+      float s = __uint_as_float(lv[e]);
+      for (int f = e + 1; f < count && lk[f] == key; ++f) s = fadd(s, __uint_as_float(lv[f]));
+      const uint32_t ch = key / span;
+      const uint32_t sk = lo + (key - ch * span);
+      const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
+      float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
+      *cell = fadd(*cell, s);
+    }
+  }
+}

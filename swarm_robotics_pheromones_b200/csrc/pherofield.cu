@@ -57,6 +57,12 @@ struct pf_handle {
   GraphKey g_key;
   uint64_t g_nodes;
   int n_sm, wave_keys, wave_agents;
+  // owner-computes deposit (pf_deposit_owner.cuh): valid after pf_agents_sort for these arrays
+  uint32_t *own_split, *own_cmin, *own_cmax, *own_pmax, *own_smin;
+  long long own_alloc;      // chunks allocated
+  long long own_n;          // agent slots the splitters were built for (0 = invalid)
+  const float* own_x;
+  int no_owner_deposit;
   long long mig_flags_n;   // > 0: scratch holds the migration flags the last move kernel wrote
   const float* mig_flags_x;
   TmaStencilState tma;
@@ -302,6 +308,11 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->buf[1]) cudaFree(h->buf[1]);
   if (h->scratch) cudaFree(h->scratch);
   if (h->cub_temp) cudaFree(h->cub_temp);
+  if (h->own_split) cudaFree(h->own_split);
+  if (h->own_cmin) cudaFree(h->own_cmin);
+  if (h->own_cmax) cudaFree(h->own_cmax);
+  if (h->own_pmax) cudaFree(h->own_pmax);
+  if (h->own_smin) cudaFree(h->own_smin);
   if (h->counters) cudaFree(h->counters);
   if (h->d_sum) cudaFree(h->d_sum);
   if (h->side) cudaStreamDestroy(h->side);
@@ -343,6 +354,13 @@ extern "C" int pf_reserve_agents(pf_handle* h, int64_t max_agents) {
   h->cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
   PF_CUDA(h, cudaMalloc(&h->cub_temp, h->cub_temp_bytes));
   h->cap = cap;
+  {  // per-chunk bounds and splitters of the owner-computes deposit
+    uint32_t** arrs[5] = {&h->own_split, &h->own_cmin, &h->own_cmax, &h->own_pmax, &h->own_smin};
+    for (auto pp : arrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    h->own_alloc = cap / kOwnChunk + 2;
+    for (auto pp : arrs) PF_CUDA(h, cudaMalloc(pp, sizeof(uint32_t) * h->own_alloc));
+    h->own_n = 0;
+  }
   return PF_OK;
 }
 
@@ -517,6 +535,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (!h) return PF_EINVAL;
   if (option == PF_OPT_OVERLAP_AGENTS) { h->overlap_agents = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_FUSED_KEYS) { h->no_fused_keys = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_NO_OWNER_DEPOSIT) { h->no_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
 }
@@ -531,6 +550,25 @@ extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_ct
 // ---------------------------------------------------------------------------------------------
 // K2 launch
 // ---------------------------------------------------------------------------------------------
+// is the owner-computes deposit usable for these agent arrays? (splitters from the last pf_agents_sort)
+static bool owner_ready(const pf_handle* h, const pf_agents* a) {
+  return !h->no_owner_deposit && !is_sharded(h) && h->own_n == a->n && h->own_x == a->x && a->n >= 4 * kOwnChunk;
+}
+
+// keys_in / vals_in (array order) -> field, without a global sort
+static int owner_sum(pf_handle* h, long long n, cudaStream_t s) {
+  h->mig_flags_n = 0;
+  const uint32_t* keys_in = (const uint32_t*)h->scratch;
+  const float* vals_in = (const float*)(keys_in + 2 * h->cap);
+  const int nchunks = (int)((n + kOwnChunk - 1) / kOwnChunk);
+  k_owner_bounds<<<1, 1024, 0, s>>>(nchunks, h->own_cmin, h->own_cmax, h->own_pmax, h->own_smin);
+  PF_LAUNCH_CHECK(h);
+  k_deposit_owner<<<nchunks, kOwnThreads, 0, s>>>(h->dev, n, nchunks, keys_in, vals_in, h->sentinel,
+                                                  h->own_split, h->own_pmax, h->own_smin, h->buf[h->cur]);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
 static int sort_and_sum(pf_handle* h, long long n, cudaStream_t s) {
   h->mig_flags_n = 0;  // the sort reuses the scratch the migration flags live in
   uint32_t* keys_in = (uint32_t*)h->scratch;
@@ -581,10 +619,13 @@ extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream)
   cudaStream_t s = (cudaStream_t)stream;
   uint32_t* keys_in = (uint32_t*)h->scratch;
   float* vals_in = (float*)(keys_in + 2 * h->cap);
+  const bool own = owner_ready(h, a);
   k_deposit_keys_agents<<<wave_grid(a->n, h->wave_keys), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, keys_in,
-                                                             vals_in, h->sentinel, h->counters);
+                                                             vals_in, h->sentinel, h->counters,
+                                                             own ? h->own_cmin : nullptr,
+                                                             own ? h->own_cmax : nullptr);
   PF_LAUNCH_CHECK(h);
-  return sort_and_sum(h, a->n, s);
+  return own ? owner_sum(h, a->n, s) : sort_and_sum(h, a->n, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -619,7 +660,9 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
   }
   k_agents_step<<<wave_grid(a->n, h->wave_agents), 256, 0, s>>>(h->dev, h->buf[h->cur], flags, a->n, a->x, a->y,
                                                      a->theta, a->wl, a->wr, a->meta, dec, h->counters, mig,
-                                                     nk, nv, h->sentinel);
+                                                     nk, nv, h->sentinel,
+                                                     (nk && owner_ready(h, a)) ? h->own_cmin : nullptr,
+                                                     (nk && owner_ready(h, a)) ? h->own_cmax : nullptr);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -729,7 +772,8 @@ static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream
     PF_CUDA(h, cudaEventRecord(pe[0], s));
   }
   if (now >= h->start_delay && (mask & PF_STEP_DEPOSIT) && a->n > 0) {  // deposit_pheromone, sup:577
-    if (keys_ready) rc = sort_and_sum(h, a->n, s);  // keys came from the previous tick's move kernel
+    if (keys_ready)  // keys came from the previous tick's move kernel
+      rc = owner_ready(h, a) ? owner_sum(h, a->n, s) : sort_and_sum(h, a->n, s);
     else rc = pf_agents_deposit(h, a, (void*)s);
     if (rc) return rc;
   }
@@ -895,6 +939,17 @@ extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
   size_t bytes = h->cub_temp_bytes;
   PF_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_temp, bytes, keys_in, keys_out, idx_in, perm, (int)n, 0,
                                              ceil_log2_u64(cells + 1), s));
+  if (!is_sharded(h) && n >= 4 * kOwnChunk) {  // splitters + fresh chunk bounds for the owner-computes deposit
+    const int nb = (int)((n + kOwnChunk - 1) / kOwnChunk);
+    const uint32_t plane = (uint32_t)((long long)h->dev.rows * h->dev.W);
+    k_owner_splitters<<<blocks_for(nb + 1, 256), 256, 0, s>>>(keys_out, n, nb, (uint32_t)((long long)h->cfg.row0 * h->cfg.W),
+                                                             plane, h->own_split);
+    PF_LAUNCH_CHECK(h);
+    PF_CUDA(h, cudaMemsetAsync(h->own_cmin, 0xff, sizeof(uint32_t) * nb, s));
+    PF_CUDA(h, cudaMemsetAsync(h->own_cmax, 0, sizeof(uint32_t) * nb, s));
+    h->own_n = n;
+    h->own_x = a->x;
+  }
   uint32_t* arrays[7] = {(uint32_t*)a->x, (uint32_t*)a->y, (uint32_t*)a->theta, (uint32_t*)a->wl,
                          (uint32_t*)a->wr, a->meta, a->gid};
   for (int k = 0; k < 7; ++k) {

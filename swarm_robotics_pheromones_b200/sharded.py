@@ -250,8 +250,10 @@ class DistDriver:
     The halo travels on a side stream while the interior rows' stencil runs; only the two edge
     rows and the agent step wait for it."""
 
-    def __init__(self, worker: StripWorker, group=None, overlap: bool = True):
+    def __init__(self, worker: StripWorker, group=None, overlap: bool = True, profile: bool = False):
         import torch.distributed as dist
+        self.profile = profile
+        self._marks = []  # per tick: list of (label, event) on the main stream
         self.dist = dist
         self.w = worker
         self.group = group
@@ -290,22 +292,41 @@ class DistDriver:
     def tick(self, sense_enabled: bool = True, move: bool = True):
         """move=False: the caller owns the poses (pf_agents_observe); nothing migrates"""
         w = self.w
+        marks = [] if (self.profile and self.cuda) else None
+
+        def mark(label):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream())
+                marks.append((label, e))
+
+        mark("start")
         w.deposit(sense_enabled)
+        mark("deposit")
         if self.overlap:
             main = torch.cuda.current_stream()
             self._comm(w.halo_sends(), w.halo_recvs(), self.ev_ready, self.ev_done)
             w.field_interior_a()                 # overlaps the halo
+            mark("stencil_a")
             main.wait_event(self.ev_done)
+            mark("wait_halo")
             w.agents(sense_enabled, move)
+            mark("agents")
             if move:
                 w.pack()
+                mark("pack")
                 self._comm(w.migrate_sends(), w.migrate_recvs(), self.ev_pack, self.ev_mig)
             w.field_rest()                       # overlaps the migration exchange
+            mark("stencil_b+edges")
             if move:
                 main.wait_event(self.ev_mig)
+                mark("wait_migration")
                 w.unpack()
+                mark("unpack")
             else:
                 w.ticks += 1
+            if marks is not None:
+                self._marks.append(marks)
             return
         for r in self._exchange(w.halo_sends(), w.halo_recvs()):
             r.wait()
@@ -320,6 +341,16 @@ class DistDriver:
             w.unpack()
         else:
             w.ticks += 1
+
+
+def phase_means(driver: "DistDriver", skip: int = 3):
+    """mean milliseconds per phase over the profiled ticks of a DistDriver (after a synchronize)"""
+    acc = {}
+    ticks = driver._marks[skip:]
+    for marks in ticks:
+        for (_, e0), (label, e1) in zip(marks[:-1], marks[1:]):
+            acc[label] = acc.get(label, 0.0) + e0.elapsed_time(e1)
+    return {k: v / max(1, len(ticks)) for k, v in acc.items()}
 
 
 def partition_agents(cfg: abi.PFConfig, world: int, x, y, theta, state=None, gid=None):

@@ -474,3 +474,70 @@ def test_graph_replay_equals_plain_launches_and_oracle():
     g2.step(sw2, 70)
     assert_bitexact(g2.snapshot(), g.snapshot())
     g.close(); g2.close()
+
+
+def test_owner_computes_deposit_hot_cells_and_long_drift():
+    """pf_agents_sort switches the agent deposit to the sort-free owner-computes kernel. Exercise its
+    overflow paths (a key range with > 2048 agents is bisected; one cell with > 2048 agents is summed
+    sequentially), two channels, and 150 ticks of drift without re-sorting; compare with the oracle
+    and with the global-sort path."""
+    cfg = make_cfg(256, 512, 2, 5, D=0.05)
+    cfg.fsm = 1
+    cfg.nest_x, cfg.nest_y = 1.28, 2.56
+    cfg.food_x[0], cfg.food_y[0] = 1.9, 3.5
+    cfg.food_radius = 0.3
+    rng = np.random.default_rng(2024)
+    n = 60000
+    x, y, th, _ = rand_agents(rng, cfg, n, margin=0.05)
+    st = rng.integers(1, 3, n)
+    # 5000 agents in ONE cell, 9000 more inside a 6 x 6 cell patch (nest-like hot spot)
+    x[:5000] = 1.2845; y[:5000] = 2.5655
+    x[5000:14000] = (1.30 + rng.uniform(0, 0.06, 9000)).astype(np.float32)
+    y[5000:14000] = (2.60 + rng.uniform(0, 0.06, 9000)).astype(np.float32)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    g2 = PheroField(cfg)
+    g2.set_option(abi.OPT_NO_OWNER_DEPOSIT, 1)
+    sw, sw2 = Swarm(x, y, th, st), Swarm(x, y, th, st)
+    g.sort_agents(sw)
+    g2.sort_agents(sw2)
+    for k in (1, 3, 30, 116):
+        o.tick(a_np, k)
+        g.step(sw, k)
+        g2.step(sw2, k)
+        assert_bitexact(g.snapshot(), o.field, f"owner-computes field after {k} more ticks")
+        assert_bitexact(g2.snapshot(), o.field, f"global-sort field after {k} more ticks")
+    got = sw.to_numpy()
+    order = np.argsort(got["gid"], kind="stable")
+    for f in ("x", "y", "theta", "wl", "wr"):
+        assert_bitexact(got[f][order], getattr(a_np, f), f)
+    assert (got["meta"][order] == a_np.meta).all()
+    assert g.counters().deposits == int(o.counters[8]) == g2.counters().deposits
+    g.close(); g2.close()
+
+
+def test_owner_computes_deposit_standalone_calls_and_fractional_amount_order():
+    # pf_agents_deposit (own key kernel) on sorted arrays, non-integer intensities: the per-cell sum
+    # order must be the array order, exactly as in the oracle's sequential sum
+    cfg = make_cfg(128, 256, 1, 0)
+    cfg.intensity_explore, cfg.intensity_high, cfg.intensity_homing = 0.3, 1.7, 0.9
+    rng = np.random.default_rng(5)
+    n = 30000
+    x, y, th, _ = rand_agents(rng, cfg, n)
+    x[:8000] = (0.5 + rng.uniform(0, 0.03, 8000)).astype(np.float32)
+    y[:8000] = (0.7 + rng.uniform(0, 0.03, 8000)).astype(np.float32)
+    st = rng.integers(1, 3, n)
+    g = PheroField(cfg)
+    sw = Swarm(x, y, th, st)
+    g.sort_agents(sw)
+    srt = sw.to_numpy()
+    a_np = dense.AgentsNP(srt["x"], srt["y"], srt["theta"], st[srt["gid"]], gid=srt["gid"])
+    a_np.meta[:] = srt["meta"]
+    o = dense.DenseOracle(cfg)
+    for _ in range(4):
+        o.agents_deposit(a_np)
+        g.agents_deposit(sw)
+    assert (sw.to_numpy()["meta"] == a_np.meta).all()
+    assert_bitexact(g.snapshot(), o.field, "fractional amounts, owner-computes vs sequential oracle")
+    g.close()
