@@ -235,7 +235,7 @@ def init_agents_torch(cfg, n, device, seed=1234):
     return x.float().numpy(), y.float().numpy(), th.float().numpy()
 
 
-def measure_other_config(name, steps, sort_every=32):
+def measure_other_config(name, steps, sort_every=16):
     """short device-resident run of another BASELINE config (reported next to the headline)"""
     import torch
 
@@ -626,7 +626,7 @@ def main():
     ap.add_argument("--rows-per-cta", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--sort-every", type=int, default=32,
+    ap.add_argument("--sort-every", type=int, default=16,
                     help="re-order the agent arrays by cell every this many ticks (0 = never)")
     ap.add_argument("--overlap-agents", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

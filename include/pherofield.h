@@ -284,8 +284,10 @@ int pf_migrate_pack(pf_handle* h, const pf_agents* a, uint32_t* up_buf, uint32_t
 /* Append the records of a received buffer into empty slots (lowest slot first, deterministic). */
 int pf_migrate_unpack(pf_handle* h, const pf_agents* a, const uint32_t* buf, int64_t cap,
                       void* stream);
-/* Same for two received buffers in one pass: all records of `buf`, then all of `buf2` (either may
- * be NULL). */
+/* Two received buffers in one pass: the records of `buf` (from the strip above: small cell keys)
+ * take the lowest empty slots in ascending order, those of `buf2` (from the strip below) the
+ * highest empty slots in descending order, so arrivals sit next to agents with similar keys and the
+ * arrays stay nearly ordered between two pf_agents_sort calls. Either buffer may be NULL. */
 int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32_t* buf, const uint32_t* buf2,
                        int64_t cap, void* stream);
 

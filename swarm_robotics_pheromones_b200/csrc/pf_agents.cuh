@@ -499,7 +499,10 @@ k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
                unsigned long long* __restrict__ counters) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  // records of `buf` first, then those of `buf2` (either may be absent)
+  // records of `buf` (from the upper neighbour: small keys) go to the LOWEST empty slots, ascending;
+  // records of `buf2` (from the lower neighbour: large keys) go to the HIGHEST empty slots,
+  // descending — arrivals land next to agents with similar cell keys (array start / end), so the
+  // arrays stay nearly ordered for the owner-computes deposit
   unsigned long long m1 = buf ? buf[0] : 0ull;
   if (m1 > (unsigned long long)cap) m1 = cap;
   unsigned long long m2 = buf2 ? buf2[0] : 0ull;
@@ -512,9 +515,16 @@ k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
     if (m > placed) atomicAdd(&counters[12], m - placed);
   }
   if (!flags[i]) return;
-  unsigned long long r = ranks[i];
-  if (r >= m) return;
-  const uint32_t* rec = (r < m1) ? buf + (r + 1) * kMigWords : buf2 + (r - m1 + 1) * kMigWords;
+  const unsigned long long r = ranks[i];
+  const unsigned long long empties = ranks[n - 1] + flags[n - 1];
+  const uint32_t* rec;
+  if (r < m1) {
+    rec = buf + (r + 1) * kMigWords;
+  } else {
+    const unsigned long long back = empties - 1 - r;  // 0 for the highest empty slot
+    if (back >= m2) return;  // stays empty (if slots run out, the ascending records keep theirs)
+    rec = buf2 + (back + 1) * kMigWords;
+  }
   ax[i] = __uint_as_float(rec[0]);
   ay[i] = __uint_as_float(rec[1]);
   ath[i] = __uint_as_float(rec[2]);

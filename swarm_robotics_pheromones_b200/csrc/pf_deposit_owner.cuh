@@ -42,12 +42,18 @@ __device__ __forceinline__ void owner_note_bounds(uint32_t* __restrict__ cmin, u
 }
 
 // prefix max of cmax, suffix min of cmin; one CTA; also resets cmin/cmax for the next tick
+// Chunks [0, body) were full of live agents at sort time (the nearly ordered body); chunks
+// [body, all) are the tail: the partly filled chunk and the empty slots behind it, where strips put
+// arriving agents. Tail chunks keep their own raw bounds (an arrival's key is unrelated to its slot
+// and must not poison the body's prefix/suffix bounds); every CTA tests them one by one.
 __global__ void __launch_bounds__(1024)
-k_owner_bounds(int nchunks, uint32_t* __restrict__ cmin, uint32_t* __restrict__ cmax,
-               uint32_t* __restrict__ pmax, uint32_t* __restrict__ smin) {
+k_owner_bounds(int all_chunks, uint32_t* __restrict__ body_chunks, uint32_t* __restrict__ cmin,
+               uint32_t* __restrict__ cmax, uint32_t* __restrict__ pmax, uint32_t* __restrict__ smin,
+               uint32_t* __restrict__ tail_list) {
   typedef cub::BlockScan<uint32_t, 1024> Scan;
   __shared__ typename Scan::TempStorage tmp;
   __shared__ uint32_t carry;
+  const int nchunks = min((int)*body_chunks, all_chunks);
   if (threadIdx.x == 0) carry = 0u;
   __syncthreads();
   for (int base = 0; base < nchunks; base += 1024) {
@@ -74,7 +80,29 @@ k_owner_bounds(int nchunks, uint32_t* __restrict__ cmin, uint32_t* __restrict__ 
     if (threadIdx.x == 1023) carry = out;
     __syncthreads();
   }
-  for (int j = threadIdx.x; j < nchunks; j += 1024) {
+  // tail: raw per-chunk bounds, and the ascending list of tail chunks that hold any key at all
+  // (body_chunks[1] = its length) so that the deposit CTAs never walk the empty rest of the arrays
+  __shared__ uint32_t ntail;
+  if (threadIdx.x == 0) ntail = 0u;
+  __syncthreads();
+  for (int base = nchunks; base < all_chunks; base += 1024) {
+    const int j = base + threadIdx.x;
+    uint32_t has = 0u;
+    if (j < all_chunks) {
+      pmax[j] = cmax[j];
+      smin[j] = cmin[j];
+      has = cmin[j] != 0xffffffffu ? 1u : 0u;
+    }
+    uint32_t off, total;
+    Scan(tmp).ExclusiveSum(has, off, total);
+    if (has) tail_list[ntail + off] = (uint32_t)j;
+    __syncthreads();
+    if (threadIdx.x == 0) ntail += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) body_chunks[1] = ntail;
+  __syncthreads();
+  for (int j = threadIdx.x; j < all_chunks; j += 1024) {
     cmin[j] = 0xffffffffu;
     cmax[j] = 0u;
   }
@@ -83,9 +111,17 @@ k_owner_bounds(int nchunks, uint32_t* __restrict__ cmin, uint32_t* __restrict__ 
 // splitters from the sorted keys of pf_agents_sort: split[b] = sorted_key[b * kOwnChunk] (offset into
 // the strip's local key space), split[0] = 0, split[nb] = plane
 __global__ void k_owner_splitters(const uint32_t* __restrict__ sorted_keys, long long n, int nb,
-                                  uint32_t key_offset, uint32_t plane, uint32_t* __restrict__ split) {
+                                  uint32_t key_offset, uint32_t plane, uint32_t empty_key,
+                                  uint32_t* __restrict__ split, uint32_t* __restrict__ body_chunks) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nb) return;
+  if (b < nb) {  // body = the prefix of chunks whose 1024 slots all hold live agents (*body_chunks preset to 0)
+    const long long last = (long long)b * kOwnChunk + kOwnChunk - 1;
+    const bool full = last < n && sorted_keys[last] != empty_key;
+    const long long nlast = last + kOwnChunk;
+    const bool next_full = (b + 1 < nb) && nlast < n && sorted_keys[nlast] != empty_key;
+    if (full && !next_full) *body_chunks = (uint32_t)(b + 1);
+  }
   uint32_t v;
   if (b == 0) v = 0u;
   else if (b == nb) v = plane;
@@ -98,9 +134,10 @@ __global__ void k_owner_splitters(const uint32_t* __restrict__ sorted_keys, long
 }
 
 __global__ void __launch_bounds__(kOwnThreads)
-k_deposit_owner(PFDev p, long long n, int nchunks, const uint32_t* __restrict__ keys,
-                const float* __restrict__ vals, uint32_t sentinel, const uint32_t* __restrict__ split,
-                const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ smin,
+k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict__ body_chunks,
+                const uint32_t* __restrict__ keys, const float* __restrict__ vals, uint32_t sentinel,
+                const uint32_t* __restrict__ split, const uint32_t* __restrict__ pmax,
+                const uint32_t* __restrict__ smin, const uint32_t* __restrict__ tail_list,
                 float* __restrict__ field) {
   typedef cub::BlockRadixSort<uint32_t, kOwnThreads, kOwnItems, uint32_t> Sort;
   typedef cub::BlockScan<int, kOwnThreads> Scan;
@@ -112,10 +149,12 @@ k_deposit_owner(PFDev p, long long n, int nchunks, const uint32_t* __restrict__ 
   __shared__ uint32_t lv[kOwnCap];  // their amounts (bit patterns)
   __shared__ uint32_t st_lo[34], st_hi[34];
   __shared__ int st_n;
+  __shared__ int tcand[kOwnThreads];  // tail chunks whose bounds meet the current key range
 
   const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
   const int b = blockIdx.x;
   const int t = threadIdx.x;
+  const int nchunks = min((int)*body_chunks, all_chunks);  // body chunks: binary-searchable bounds
   if (t == 0) {
     st_lo[0] = split[b];
     st_hi[0] = split[b + 1];
@@ -142,7 +181,29 @@ k_deposit_owner(PFDev p, long long n, int nchunks, const uint32_t* __restrict__ 
     __syncthreads();
     const uint32_t span = hi - lo;
     int count = 0;
-    for (int j = j0; j <= j1; ++j) {
+    // candidates: body chunks j0..j1 (phase 0), then, 256 at a time, the non-empty tail chunks whose
+    // own bounds meet [lo, hi) (ascending: array order is preserved)
+    const int nt = (int)body_chunks[1];
+    const int nphase = 1 + (nt + kOwnThreads - 1) / kOwnThreads;
+    const int nbody = (j1 - j0 + 1 > 0 ? j1 - j0 + 1 : 0);
+    for (int phase = 0; phase < nphase; ++phase) {
+    int ncand = nbody;
+    if (phase > 0) {
+      const int it = (phase - 1) * kOwnThreads + t;
+      int has = 0, jt = 0;
+      if (it < nt) {
+        jt = (int)tail_list[it];
+        has = (pmax[jt] >= lo && smin[jt] < hi) ? 1 : 0;
+      }
+      int off, total;
+      __syncthreads();
+      Scan(tmp.scan).ExclusiveSum(has, off, total);
+      if (has) tcand[off] = jt;
+      __syncthreads();
+      ncand = total;
+    }
+    for (int c = 0; c < ncand; ++c) {
+      const int j = phase == 0 ? j0 + c : tcand[c];
       const long long e0 = (long long)j * kOwnChunk + 4 * t;
       uint32_t k4[4], v4[4];
       int sel[4], nsel = 0;
@@ -175,6 +236,7 @@ k_deposit_owner(PFDev p, long long n, int nchunks, const uint32_t* __restrict__ 
       }
       count += total;
     }
+    }  // phases
     __syncthreads();
 
     if (count == 0) continue;
@@ -192,7 +254,24 @@ k_deposit_owner(PFDev p, long long n, int nchunks, const uint32_t* __restrict__ 
         float s = 0.0f;
         bool any = false;
         const uint32_t want = (uint32_t)ch * plane + lo;
-        for (int j = j0; j <= j1; ++j) {
+        for (int phase = 0; phase < nphase; ++phase) {
+        int ncand = nbody;
+        if (phase > 0) {
+          const int it = (phase - 1) * kOwnThreads + t;
+          int has = 0, jt = 0;
+          if (it < nt) {
+            jt = (int)tail_list[it];
+            has = (pmax[jt] >= lo && smin[jt] < hi) ? 1 : 0;
+          }
+          int off, total;
+          __syncthreads();
+          Scan(tmp.scan).ExclusiveSum(has, off, total);
+          if (has) tcand[off] = jt;
+          __syncthreads();
+          ncand = total;
+        }
+        for (int c = 0; c < ncand; ++c) {
+          const int j = phase == 0 ? j0 + c : tcand[c];
           const long long e0 = (long long)j * kOwnChunk + 4 * t;
           int nsel = 0;
           uint32_t v4[4];
@@ -214,6 +293,7 @@ k_deposit_owner(PFDev p, long long n, int nchunks, const uint32_t* __restrict__ 
             }
           __syncthreads();
         }
+        }  // phases
         if (t == 0 && any) {
           const int lr = (int)(lo / (uint32_t)p.W), col = (int)(lo - (uint32_t)lr * (uint32_t)p.W);
           float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;

@@ -58,7 +58,7 @@ struct pf_handle {
   uint64_t g_nodes;
   int n_sm, wave_keys, wave_agents;
   // owner-computes deposit (pf_deposit_owner.cuh): valid after pf_agents_sort for these arrays
-  uint32_t *own_split, *own_cmin, *own_cmax, *own_pmax, *own_smin;
+  uint32_t *own_split, *own_cmin, *own_cmax, *own_pmax, *own_smin, *own_body, *own_tail;
   long long own_alloc;      // chunks allocated
   long long own_n;          // agent slots the splitters were built for (0 = invalid)
   const float* own_x;
@@ -313,6 +313,8 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->own_cmax) cudaFree(h->own_cmax);
   if (h->own_pmax) cudaFree(h->own_pmax);
   if (h->own_smin) cudaFree(h->own_smin);
+  if (h->own_body) cudaFree(h->own_body);
+  if (h->own_tail) cudaFree(h->own_tail);
   if (h->counters) cudaFree(h->counters);
   if (h->d_sum) cudaFree(h->d_sum);
   if (h->side) cudaStreamDestroy(h->side);
@@ -355,7 +357,8 @@ extern "C" int pf_reserve_agents(pf_handle* h, int64_t max_agents) {
   PF_CUDA(h, cudaMalloc(&h->cub_temp, h->cub_temp_bytes));
   h->cap = cap;
   {  // per-chunk bounds and splitters of the owner-computes deposit
-    uint32_t** arrs[5] = {&h->own_split, &h->own_cmin, &h->own_cmax, &h->own_pmax, &h->own_smin};
+    uint32_t** arrs[7] = {&h->own_split, &h->own_cmin, &h->own_cmax, &h->own_pmax, &h->own_smin, &h->own_body,
+                          &h->own_tail};
     for (auto pp : arrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     h->own_alloc = cap / kOwnChunk + 2;
     for (auto pp : arrs) PF_CUDA(h, cudaMalloc(pp, sizeof(uint32_t) * h->own_alloc));
@@ -552,7 +555,7 @@ extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_ct
 // ---------------------------------------------------------------------------------------------
 // is the owner-computes deposit usable for these agent arrays? (splitters from the last pf_agents_sort)
 static bool owner_ready(const pf_handle* h, const pf_agents* a) {
-  return !h->no_owner_deposit && !is_sharded(h) && h->own_n == a->n && h->own_x == a->x && a->n >= 4 * kOwnChunk;
+  return !h->no_owner_deposit && h->own_n == a->n && h->own_x == a->x && a->n >= 4 * kOwnChunk;
 }
 
 // keys_in / vals_in (array order) -> field, without a global sort
@@ -561,10 +564,12 @@ static int owner_sum(pf_handle* h, long long n, cudaStream_t s) {
   const uint32_t* keys_in = (const uint32_t*)h->scratch;
   const float* vals_in = (const float*)(keys_in + 2 * h->cap);
   const int nchunks = (int)((n + kOwnChunk - 1) / kOwnChunk);
-  k_owner_bounds<<<1, 1024, 0, s>>>(nchunks, h->own_cmin, h->own_cmax, h->own_pmax, h->own_smin);
+  k_owner_bounds<<<1, 1024, 0, s>>>(nchunks, h->own_body, h->own_cmin, h->own_cmax, h->own_pmax, h->own_smin,
+                                    h->own_tail);
   PF_LAUNCH_CHECK(h);
-  k_deposit_owner<<<nchunks, kOwnThreads, 0, s>>>(h->dev, n, nchunks, keys_in, vals_in, h->sentinel,
-                                                  h->own_split, h->own_pmax, h->own_smin, h->buf[h->cur]);
+  k_deposit_owner<<<nchunks, kOwnThreads, 0, s>>>(h->dev, n, nchunks, h->own_body, keys_in, vals_in, h->sentinel,
+                                                  h->own_split, h->own_pmax, h->own_smin, h->own_tail,
+                                                  h->buf[h->cur]);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -939,11 +944,12 @@ extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
   size_t bytes = h->cub_temp_bytes;
   PF_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_temp, bytes, keys_in, keys_out, idx_in, perm, (int)n, 0,
                                              ceil_log2_u64(cells + 1), s));
-  if (!is_sharded(h) && n >= 4 * kOwnChunk) {  // splitters + fresh chunk bounds for the owner-computes deposit
+  if (n >= 4 * kOwnChunk) {  // splitters + fresh chunk bounds for the owner-computes deposit
     const int nb = (int)((n + kOwnChunk - 1) / kOwnChunk);
     const uint32_t plane = (uint32_t)((long long)h->dev.rows * h->dev.W);
+    PF_CUDA(h, cudaMemsetAsync(h->own_body, 0, 2 * sizeof(uint32_t), s));
     k_owner_splitters<<<blocks_for(nb + 1, 256), 256, 0, s>>>(keys_out, n, nb, (uint32_t)((long long)h->cfg.row0 * h->cfg.W),
-                                                             plane, h->own_split);
+                                                             plane, sentinel, h->own_split, h->own_body);
     PF_LAUNCH_CHECK(h);
     PF_CUDA(h, cudaMemsetAsync(h->own_cmin, 0xff, sizeof(uint32_t) * nb, s));
     PF_CUDA(h, cudaMemsetAsync(h->own_cmax, 0, sizeof(uint32_t) * nb, s));

@@ -76,20 +76,22 @@ class OracleStrip:
             a.meta[idx] = abi.STATE_EMPTY
 
     def unpack(self, from_up, from_down):
+        """arrivals from the upper neighbour take the lowest empty slots (ascending), arrivals from the
+        lower neighbour the highest ones (descending) — the library's placement rule"""
         a = self.a
-        # arrivals from the upper neighbour first, then from the lower one, lowest empty slot first
-        for use, buf in ((from_up, self.recv_up), (from_down, self.recv_down)):
+        for use, buf, from_top in ((from_up, self.recv_up, True), (from_down, self.recv_down, False)):
             if not use:
                 continue
+            empty = np.nonzero((a.meta & 3) == 0)[0]
             inp = buf.numpy().view(np.uint32)
             m = int(inp[0])
             rec = inp[W8:].reshape(-1, W8)[:m]
-            empty = np.nonzero((a.meta & 3) == 0)[0][:m]
-            assert len(empty) == m, "no empty slot left"
+            slots = empty[:m] if from_top else empty[::-1][:m]
+            assert len(slots) == m, "no empty slot left"
             for k, f in enumerate(("x", "y", "theta", "wl", "wr")):
-                getattr(a, f)[empty] = rec[:, k].view(np.float32)
-            a.meta[empty] = rec[:, 5]
-            a.gid[empty] = rec[:, 6]
+                getattr(a, f)[slots] = rec[:, k].view(np.float32)
+            a.meta[slots] = rec[:, 5]
+            a.gid[slots] = rec[:, 6]
 
     def synchronize(self):
         pass

@@ -22,6 +22,7 @@ ap.add_argument("--ticks", type=int, default=100)
 ap.add_argument("--grid", type=int, default=2048)
 ap.add_argument("--agents", type=int, default=200000)
 ap.add_argument("--no-overlap", action="store_true")
+ap.add_argument("--sort-every", type=int, default=16)
 args = ap.parse_args()
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -52,7 +53,9 @@ scfg = sharded.strip_config(cfg, world, rank, device=local)
 strip = sharded.CudaStrip(scfg, p["x"], p["y"], p["theta"], p["state"], p["gid"],
                           capacity=int(len(p["x"]) * 1.5) + 1024, migrate_cap=8192)
 drv = sharded.DistDriver(sharded.StripWorker(strip, rank, world), overlap=not args.no_overlap)
-for _ in range(args.ticks):
+for t in range(args.ticks):
+    if args.sort_every and t % args.sort_every == 0:
+        strip.sort_agents()
     drv.tick(True)
 torch.cuda.synchronize()
 
