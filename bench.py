@@ -580,6 +580,10 @@ def run_sharded(args):
     allc = [torch.zeros_like(counts) for _ in range(world)]
     dist.all_gather(allc, counts)
 
+    phases_all = None
+    if args.phase_profile:
+        phases_all = [None] * world
+        dist.all_gather_object(phases_all, sharded.phase_means(drv))
     if rank == 0:
         line = {
             "metric": "grid cell-updates/s (agent-steps/s alongside)",
@@ -604,7 +608,8 @@ def run_sharded(args):
             "agent_sort_every": args.sort_every,
         }
         if args.phase_profile:
-            line["phase_ms_rank0"] = sharded.phase_means(drv)
+            line["phase_ms_rank0"] = phases_all[0]
+            line["phase_ms_all_ranks"] = phases_all
         print(json.dumps(line), flush=True)
     dist.barrier()
     strip.field.close()

@@ -484,11 +484,33 @@ k_migrate_scatter(long long n, long long cap, const unsigned long long* __restri
   ameta[i] = PF_STATE_EMPTY;
 }
 
+// Placement order of arriving agents. After pf_agents_sort the arrays are [body (ordered by cell) |
+// tail (empty)]. Agents only ever leave from the two ends of the body, so the holes sit there.
+// Candidate slots are ranked in the order  [first half of the body | tail | second half of the body]:
+// arrivals from the strip above (small keys) take ranks ascending — holes at the start of the body,
+// then the tail; arrivals from the strip below (large keys) take ranks descending — holes at the end
+// of the body, then the tail from its far end. An arrival therefore never lands among agents whose
+// keys are far from its own, which would widen the chunk bounds of the owner-computes deposit.
+__device__ __forceinline__ long long mig_slot_of_rank_index(long long ip, long long n, long long T, long long M) {
+  if (ip < M) return ip;
+  if (ip < M + (n - T)) return T + (ip - M);
+  return M + (ip - M - (n - T));
+}
+__device__ __forceinline__ void mig_body_split(const uint32_t* body_chunks, long long n, long long& T, long long& M) {
+  T = body_chunks ? (long long)body_chunks[0] * kOwnChunk : 0;
+  if (T > n) T = n;
+  M = (T / 2) / kOwnChunk * kOwnChunk;
+}
+
 __global__ void __launch_bounds__(256)
-k_empty_flags(long long n, const uint32_t* __restrict__ meta, unsigned long long* __restrict__ flags) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  flags[i] = ((meta[i] & PF_META_STATE_MASK) == PF_STATE_EMPTY) ? 1ull : 0ull;
+k_empty_flags(long long n, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ body_chunks,
+              unsigned long long* __restrict__ flags) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= n) return;
+  long long T, M;
+  mig_body_split(body_chunks, n, T, M);
+  const long long i = mig_slot_of_rank_index(ip, n, T, M);
+  flags[ip] = ((meta[i] & PF_META_STATE_MASK) == PF_STATE_EMPTY) ? 1ull : 0ull;
 }
 
 __global__ void __launch_bounds__(256)
@@ -496,26 +518,27 @@ k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
                const unsigned long long* __restrict__ ranks, const uint32_t* __restrict__ buf,
                const uint32_t* __restrict__ buf2, long long cap, float* ax, float* ay, float* ath,
                float* awl, float* awr, uint32_t* ameta, uint32_t* agid,
-               unsigned long long* __restrict__ counters) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  // records of `buf` (from the upper neighbour: small keys) go to the LOWEST empty slots, ascending;
-  // records of `buf2` (from the lower neighbour: large keys) go to the HIGHEST empty slots,
-  // descending — arrivals land next to agents with similar cell keys (array start / end), so the
-  // arrays stay nearly ordered for the owner-computes deposit
+               unsigned long long* __restrict__ counters, const uint32_t* __restrict__ body_chunks) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= n) return;
+  long long T, M;
+  mig_body_split(body_chunks, n, T, M);
+  const long long i = mig_slot_of_rank_index(ip, n, T, M);  // slot this rank index stands for
+  // records of `buf` (from the strip above) take candidate ranks ascending, records of `buf2` (from
+  // the strip below) descending — see mig_slot_of_rank_index
   unsigned long long m1 = buf ? buf[0] : 0ull;
   if (m1 > (unsigned long long)cap) m1 = cap;
   unsigned long long m2 = buf2 ? buf2[0] : 0ull;
   if (m2 > (unsigned long long)cap) m2 = cap;
   const unsigned long long m = m1 + m2;
-  if (i == n - 1) {
-    unsigned long long empties = ranks[i] + flags[i];
+  if (ip == n - 1) {
+    unsigned long long empties = ranks[ip] + flags[ip];
     unsigned long long placed = m < empties ? m : empties;
     atomicAdd(&counters[11], placed);
     if (m > placed) atomicAdd(&counters[12], m - placed);
   }
-  if (!flags[i]) return;
-  const unsigned long long r = ranks[i];
+  if (!flags[ip]) return;
+  const unsigned long long r = ranks[ip];
   const unsigned long long empties = ranks[n - 1] + flags[n - 1];
   const uint32_t* rec;
   if (r < m1) {

@@ -1018,12 +1018,14 @@ extern "C" int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32
   cudaStream_t s = (cudaStream_t)stream;
   unsigned long long* flags = (unsigned long long*)h->scratch;
   unsigned long long* ranks = flags + h->cap;
-  k_empty_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, a->meta, flags);
+  // the body/tail split of the last pf_agents_sort of these arrays steers where arrivals are put
+  const uint32_t* body = (h->own_n == a->n && h->own_x == a->x) ? h->own_body : nullptr;
+  k_empty_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, a->meta, body, flags);
   PF_LAUNCH_CHECK(h);
   size_t bytes = h->cub_temp_bytes;
   PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
   k_migrate_fill<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, flags, ranks, buf, buf2, cap, a->x, a->y, a->theta,
-                                                      a->wl, a->wr, a->meta, a->gid, h->counters);
+                                                      a->wl, a->wr, a->meta, a->gid, h->counters, body);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }

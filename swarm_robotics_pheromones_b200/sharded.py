@@ -344,13 +344,13 @@ class DistDriver:
 
 
 def phase_means(driver: "DistDriver", skip: int = 3):
-    """mean milliseconds per phase over the profiled ticks of a DistDriver (after a synchronize)"""
+    """median milliseconds per phase over the profiled ticks of a DistDriver (after a synchronize);
+    the median keeps one-off costs (NCCL connection set-up on the first exchanges) out"""
     acc = {}
-    ticks = driver._marks[skip:]
-    for marks in ticks:
+    for marks in driver._marks[skip:]:
         for (_, e0), (label, e1) in zip(marks[:-1], marks[1:]):
-            acc[label] = acc.get(label, 0.0) + e0.elapsed_time(e1)
-    return {k: v / max(1, len(ticks)) for k, v in acc.items()}
+            acc.setdefault(label, []).append(e0.elapsed_time(e1))
+    return {k: float(np.median(v)) for k, v in acc.items()}
 
 
 def partition_agents(cfg: abi.PFConfig, world: int, x, y, theta, state=None, gid=None):
