@@ -363,6 +363,8 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
 #define PF_OPT_OVERLAP_AGENTS 1 /* pf_step: run sense/decide/move on a side stream beside the stencil */
 #define PF_OPT_NO_FUSED_KEYS 2  /* pf_step: always build deposit keys in their own kernel */
 #define PF_OPT_NO_OWNER_DEPOSIT 4 /* always use the global radix sort for the agent deposit */
+#define PF_OPT_FORCE_OWNER_DEPOSIT 5 /* use the sort-free deposit after pf_agents_sort even where the
+                                        density heuristic prefers the radix sort (dense clusters) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */
 int pf_set_option(pf_handle* h, int option, int value);

@@ -120,7 +120,11 @@ __global__ void k_owner_splitters(const uint32_t* __restrict__ sorted_keys, long
     const bool full = last < n && sorted_keys[last] != empty_key;
     const long long nlast = last + kOwnChunk;
     const bool next_full = (b + 1 < nb) && nlast < n && sorted_keys[nlast] != empty_key;
-    if (full && !next_full) *body_chunks = (uint32_t)(b + 1);
+    if (full && !next_full) {
+      *body_chunks = (uint32_t)(b + 1);
+      body_chunks[3] = sorted_keys[last];  // (about) the largest live key: density estimate for the host
+    }
+    if (b == 0) body_chunks[2] = sorted_keys[0];
   }
   uint32_t v;
   if (b == 0) v = 0u;

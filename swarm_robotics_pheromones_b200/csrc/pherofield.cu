@@ -63,6 +63,9 @@ struct pf_handle {
   long long own_n;          // agent slots the splitters were built for (0 = invalid)
   const float* own_x;
   int no_owner_deposit;
+  int force_owner_deposit;
+  int own_worth;              // host heuristic from the last pf_agents_sort (see there)
+  double own_scan_estimate;
   long long mig_flags_n;   // > 0: scratch holds the migration flags the last move kernel wrote
   const float* mig_flags_x;
   TmaStencilState tma;
@@ -539,6 +542,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_OVERLAP_AGENTS) { h->overlap_agents = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_FUSED_KEYS) { h->no_fused_keys = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_OWNER_DEPOSIT) { h->no_owner_deposit = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_FORCE_OWNER_DEPOSIT) { h->force_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
 }
@@ -555,7 +559,8 @@ extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_ct
 // ---------------------------------------------------------------------------------------------
 // is the owner-computes deposit usable for these agent arrays? (splitters from the last pf_agents_sort)
 static bool owner_ready(const pf_handle* h, const pf_agents* a) {
-  return !h->no_owner_deposit && h->own_n == a->n && h->own_x == a->x && a->n >= 4 * kOwnChunk;
+  return !h->no_owner_deposit && (h->own_worth || h->force_owner_deposit) && h->own_n == a->n &&
+         h->own_x == a->x && a->n >= 4 * kOwnChunk && (a->n >= 64 * kOwnChunk || h->force_owner_deposit);
 }
 
 // keys_in / vals_in (array order) -> field, without a global sort
@@ -947,7 +952,7 @@ extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
   if (n >= 4 * kOwnChunk) {  // splitters + fresh chunk bounds for the owner-computes deposit
     const int nb = (int)((n + kOwnChunk - 1) / kOwnChunk);
     const uint32_t plane = (uint32_t)((long long)h->dev.rows * h->dev.W);
-    PF_CUDA(h, cudaMemsetAsync(h->own_body, 0, 2 * sizeof(uint32_t), s));
+    PF_CUDA(h, cudaMemsetAsync(h->own_body, 0, 4 * sizeof(uint32_t), s));
     k_owner_splitters<<<blocks_for(nb + 1, 256), 256, 0, s>>>(keys_out, n, nb, (uint32_t)((long long)h->cfg.row0 * h->cfg.W),
                                                              plane, sentinel, h->own_split, h->own_body);
     PF_LAUNCH_CHECK(h);
@@ -955,6 +960,19 @@ extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
     PF_CUDA(h, cudaMemsetAsync(h->own_cmax, 0, sizeof(uint32_t) * nb, s));
     h->own_n = n;
     h->own_x = a->x;
+    {  // Is the sort-free deposit worth it here? A CTA re-scans about 1 + 2*drift_rows*agents_per_row/1024
+       // array chunks; in dense clusters (thousands of agents per populated row) the global radix sort
+       // is cheaper. One small synchronous read-back per pf_agents_sort.
+      uint32_t st[4] = {0, 0, 0, 0};
+      PF_CUDA(h, cudaMemcpyAsync(st, h->own_body, sizeof(st), cudaMemcpyDeviceToHost, s));
+      PF_CUDA(h, cudaStreamSynchronize(s));
+      const double alive = (double)st[0] * kOwnChunk;
+      const double rows_pop = (double)(st[3] - st[2]) / (double)h->cfg.W + 1.0;
+      const double per_row = alive > 0 ? alive / rows_pop : 0.0;
+      const double drift_rows = 2.7;  // ~0.33 cells per tick over half of a 16-tick re-sort interval
+      h->own_scan_estimate = 1.0 + 2.0 * drift_rows * per_row / kOwnChunk;
+      h->own_worth = (st[0] > 0 && h->own_scan_estimate <= 8.0) ? 1 : 0;
+    }
   }
   uint32_t* arrays[7] = {(uint32_t*)a->x, (uint32_t*)a->y, (uint32_t*)a->theta, (uint32_t*)a->wl,
                          (uint32_t*)a->wr, a->meta, a->gid};

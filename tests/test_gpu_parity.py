@@ -497,6 +497,7 @@ def test_owner_computes_deposit_hot_cells_and_long_drift():
     a_np = dense.AgentsNP(x, y, th, st)
     o = dense.DenseOracle(cfg)
     g = PheroField(cfg)
+    g.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)  # dense on purpose: the heuristic would pick the radix sort
     g2 = PheroField(cfg)
     g2.set_option(abi.OPT_NO_OWNER_DEPOSIT, 1)
     sw, sw2 = Swarm(x, y, th, st), Swarm(x, y, th, st)
@@ -529,6 +530,7 @@ def test_owner_computes_deposit_standalone_calls_and_fractional_amount_order():
     y[:8000] = (0.7 + rng.uniform(0, 0.03, 8000)).astype(np.float32)
     st = rng.integers(1, 3, n)
     g = PheroField(cfg)
+    g.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
     sw = Swarm(x, y, th, st)
     g.sort_agents(sw)
     srt = sw.to_numpy()

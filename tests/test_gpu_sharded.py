@@ -27,6 +27,7 @@ def test_strips_equal_unsharded_bitexact(world, variant):
         strip = sharded.CudaStrip(sharded.strip_config(cfg, world, r), p["x"], p["y"], p["theta"],
                                   p["state"], p["gid"], capacity=6000, migrate_cap=512)
         strip.field.set_stencil_variant(variant, 8)
+        strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)  # small dense test arena
         workers.append(sharded.StripWorker(strip, r, world))
     drv = sharded.LocalDriver(workers)
     for t in range(nticks):
