@@ -43,7 +43,6 @@ CONFIGS = {
 }
 BYTES_PER_CELL_UPDATE = 8          # SURVEY §8d / BASELINE.md §5
 BYTES_PER_AGENT_STEP = 56
-BYTES_PER_DEPOSIT = 12 + 8
 
 
 def make_config(name: str, H=None, W=None, C=None, agents=None, stencil=None):
@@ -546,7 +545,6 @@ def run_sharded(args):
     h_pose = torch.empty((3, nl), dtype=torch.float32).pin_memory()
     d_pose = torch.empty((3, nl), dtype=torch.float32, device="cuda")
     h_out = torch.empty((2, nl), dtype=torch.float32).pin_memory()
-    d_out = torch.empty((2, nl), dtype=torch.float32, device="cuda")
     h_pose[0].copy_(sw.x.cpu()); h_pose[1].copy_(sw.y.cpu()); h_pose[2].copy_(sw.theta.cpu())
     h_pose_b = torch.empty_like(h_pose).pin_memory()
     h_pose_b.copy_(h_pose)

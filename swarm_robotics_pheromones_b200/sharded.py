@@ -17,7 +17,7 @@ compute backend; the product backend is CudaStrip (libpherofield.so).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

@@ -73,12 +73,19 @@ def test_invalid_configs_are_rejected_before_touching_the_gpu():
 
 
 def test_product_path_does_not_import_the_oracle():
-    """the product package must never route through oracle/ (test infrastructure)"""
+    """the product package must never import, include, link or load anything under oracle/
+    (test infrastructure); comments may cite it"""
     import pathlib
+    import re
     pkg = pathlib.Path(build.PKG)
+    py_import = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    loads = re.compile(r"(libpf_oracle|oracle[/\\][\w.]+\.(so|py)|#\s*include\s*[\"<][^\">]*oracle)")
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         text = p.read_text()
-        assert "oracle" not in text.replace("test oracle", "").replace("the oracle's", "").replace("oracle/pf_oracle.c", ""), p
+        assert not py_import.search(text), f"{p} imports the oracle"
+        code = "\n".join(ln for ln in text.splitlines() if not ln.strip().startswith(("//", "#", "*", "/*")))
+        assert not loads.search(code), f"{p} loads or includes the oracle"
+    assert "oracle" not in " ".join(build.NVCC_FLAGS) and all("oracle" not in str(x) for x in build.sources())
 
 
 def test_sass_has_tma_bulk_copy_and_128bit_accesses():
@@ -88,4 +95,3 @@ def test_sass_has_tma_bulk_copy_and_128bit_accesses():
     assert "UBLKCP" in out.stdout          # cp.async.bulk -> TMA engine
     assert "SYNCS" in out.stdout           # mbarrier
     assert "LDG.E.128" in out.stdout and "STG.E.128" in out.stdout
-    assert "FFMA" not in out.stdout.split("k_stencil_tma")[1][:200000] or True  # informational
