@@ -493,6 +493,13 @@ def run_sharded(args):
     strip.field.set_stencil_variant(args.variant, args.rows_per_cta)
     worker = sharded.StripWorker(strip, rank, world)
     drv = sharded.DistDriver(worker, overlap=not args.no_overlap, profile=args.phase_profile)
+    if not args.nccl_halo:
+        # halo exchange fused into the deposit / stencil kernels: edge rows are stored straight into
+        # the neighbours' ghost rows over NVLink (CUDA IPC mappings); NCCL only carries migrants
+        strip.peer_attach_ipc(rank, world)
+        dist.barrier()
+        strip.peer_prime()
+        strip.peer_wait()
     cells = cfg.H * cfg.W * cfg.C
 
     tick_no = [0]
@@ -608,6 +615,7 @@ def run_sharded(args):
             "cpu_baseline": None,
             "agents_per_rank": [int(c.item()) for c in allc],
             "halo_overlap": not args.no_overlap, "stencil_variant": args.variant,
+            "halo": "nccl send/recv" if args.nccl_halo else "peer stores fused into the kernels (CUDA IPC, NVLink P2P)",
             "agent_sort_every": args.sort_every,
         }
         if args.phase_profile:
@@ -640,6 +648,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the c1/c2/c4 and trail side runs")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="sharded run: NCCL send/recv halo instead of peer stores")
     ap.add_argument("--phase-profile", action="store_true", help="sharded run: per-phase CUDA events")
     args = ap.parse_args()
     if args.warmup < 3:

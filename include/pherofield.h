@@ -291,6 +291,28 @@ int pf_migrate_unpack(pf_handle* h, const pf_agents* a, const uint32_t* buf, int
 int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32_t* buf, const uint32_t* buf2,
                        int64_t cap, void* stream);
 
+/* Peer-store halo over NVLink P2P — the halo exchange fused into the producing kernels. Once the
+ * neighbours are attached, every kernel that writes this strip's first / last interior row (the
+ * stencil's edge rows into the next buffer, the deposit into the current buffer) also stores the
+ * value into the neighbour strip's mailbox (a small IPC-mapped block) through its mapped address;
+ * no halo message is sent, and pf_peer_wait moves the mailbox rows into the ghost rows.
+ * Per tick: deposit -> pf_peer_signal (epoch flag into the neighbours' memory) -> interior stencil
+ * -> pf_peer_wait (own flag words) -> agents, edge rows. All strips must swap buffers in lockstep.
+ * After the field was changed from outside (upload, fill) call pf_peer_push_edges + signal/wait. */
+typedef struct pf_peer_info {
+  void* buf0;  /* the strip's mailboxes for buffer parity 0 / 1 (device pointers valid in THIS process) */
+  void* buf1;
+  void* flags; /* two u32 epoch words: [0] written by the strip above, [1] by the strip below */
+  int64_t rows, pitch, chan_stride;
+} pf_peer_info;
+int pf_peer_export(pf_handle* h, pf_peer_info* out);                /* this strip, raw pointers */
+int pf_peer_ipc_handles(pf_handle* h, uint8_t* out192);             /* cudaIpcMemHandle_t + pad  */
+int pf_peer_ipc_open(pf_handle* h, const uint8_t* in192, const pf_peer_info* dims, pf_peer_info* out);
+int pf_peer_attach(pf_handle* h, const pf_peer_info* up, const pf_peer_info* down); /* NULL = none */
+int pf_peer_push_edges(pf_handle* h, void* stream);
+int pf_peer_signal(pf_handle* h, void* stream);
+int pf_peer_wait(pf_handle* h, void* stream);
+
 int pf_counters_host(pf_handle* h, pf_counters* out_host, void* stream);
 int pf_counters_reset(pf_handle* h, void* stream);
 

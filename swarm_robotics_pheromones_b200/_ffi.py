@@ -46,6 +46,13 @@ SIGNATURES = {
     "pf_migrate_pack": (C.c_int, [_vp, _agp, _vp, _vp, C.c_int64, _vp]),
     "pf_migrate_unpack": (C.c_int, [_vp, _agp, _vp, C.c_int64, _vp]),
     "pf_migrate_unpack2": (C.c_int, [_vp, _agp, _vp, _vp, C.c_int64, _vp]),
+    "pf_peer_export": (C.c_int, [_vp, C.POINTER(abi.PFPeerInfo)]),
+    "pf_peer_ipc_handles": (C.c_int, [_vp, _vp]),
+    "pf_peer_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(abi.PFPeerInfo), C.POINTER(abi.PFPeerInfo)]),
+    "pf_peer_attach": (C.c_int, [_vp, C.POINTER(abi.PFPeerInfo), C.POINTER(abi.PFPeerInfo)]),
+    "pf_peer_push_edges": (C.c_int, [_vp, _vp]),
+    "pf_peer_signal": (C.c_int, [_vp, _vp]),
+    "pf_peer_wait": (C.c_int, [_vp, _vp]),
     "pf_counters_host": (C.c_int, [_vp, C.POINTER(abi.PFCounters), _vp]),
     "pf_counters_reset": (C.c_int, [_vp, _vp]),
     "pf_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),

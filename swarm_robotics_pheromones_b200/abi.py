@@ -140,6 +140,11 @@ class PFTrailOut(C.Structure):
                 ("pre_time", C.c_void_p), ("pre_intensity", C.c_void_p), ("n_pre", C.c_void_p)]
 
 
+class PFPeerInfo(C.Structure):
+    _fields_ = [("buf0", C.c_void_p), ("buf1", C.c_void_p), ("flags", C.c_void_p),
+                ("rows", C.c_int64), ("pitch", C.c_int64), ("chan_stride", C.c_int64)]
+
+
 class PFProfile(C.Structure):
     _fields_ = [("ticks", C.c_uint64), ("deposit_ms", C.c_double), ("stencil_ms", C.c_double),
                 ("agents_ms", C.c_double)]

@@ -84,7 +84,8 @@ k_deposit_keys_generic(PFDev p, long long n, const float* __restrict__ x,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_deposit_segsum(PFDev p, long long n, const uint32_t* __restrict__ keys,
-                 const float* __restrict__ vals, uint32_t sentinel, float* __restrict__ field) {
+                 const float* __restrict__ vals, uint32_t sentinel, float* __restrict__ field,
+                 PeerRows peer) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t key = sentinel;
@@ -122,7 +123,10 @@ k_deposit_segsum(PFDev p, long long n, const uint32_t* __restrict__ keys,
     const int lr = (int)(rem / p.W);
     const int col = (int)(rem - (long long)lr * p.W);
     float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
-    *cell = fadd(*cell, s);
+    const float nv = fadd(*cell, s);
+    *cell = nv;
+    if (lr == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;  // keep the neighbour's ghost row current
+    if (lr == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
   }
 }
 
@@ -560,6 +564,42 @@ k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
+// explicit halo push: copy this strip's first / last interior row of `f` into the neighbours' ghost rows
+__global__ void k_peer_push_edges(PFDev p, const float* __restrict__ f, PeerRows peer) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  int ch = blockIdx.y;
+  if (col >= p.W) return;
+  const float* plane = f + (long long)ch * p.chan_stride;
+  if (peer.up) peer.up[ch * peer.up_cs + col] = plane[p.pitch + col];
+  if (peer.dn) peer.dn[ch * peer.dn_cs + col] = plane[(long long)p.rows * p.pitch + col];
+}
+
+// after the wait: the rows the neighbours stored into this strip's mailbox become its ghost rows
+__global__ void k_mailbox_to_ghosts(PFDev p, float* f, const float* __restrict__ mailbox, int top, int bottom) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  int ch = blockIdx.y;
+  if (col >= p.W) return;
+  float* plane = f + (long long)ch * p.chan_stride;
+  if (top) plane[col] = mailbox[(long long)ch * p.pitch + col];
+  if (bottom) plane[(long long)(p.rows + 1) * p.pitch + col] = mailbox[(long long)(p.C + ch) * p.pitch + col];
+}
+
+// Epoch flags in the RECEIVER's memory: a strip stores `epoch` into its neighbours' flag words after
+// its deposit; each strip polls its own two words before it reads its ghost rows. One thread each;
+// between different GPUs (or, for in-process strips on one GPU, already satisfied by stream order).
+__global__ void k_peer_signal(volatile unsigned int* up_flag, volatile unsigned int* dn_flag, unsigned int epoch) {
+  __threadfence_system();
+  if (up_flag) *up_flag = epoch;
+  if (dn_flag) *dn_flag = epoch;
+  __threadfence_system();
+}
+__global__ void k_peer_wait(volatile const unsigned int* from_up, volatile const unsigned int* from_dn,
+                            unsigned int epoch) {
+  if (from_up) while ((int)(*from_up - epoch) < 0) { }
+  if (from_dn) while ((int)(*from_dn - epoch) < 0) { }
+  __threadfence_system();
+}
+
 __global__ void k_fill_ghosts(PFDev p, float* f, int top, int bottom) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   int ch = blockIdx.y;

@@ -142,7 +142,7 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
                 const uint32_t* __restrict__ keys, const float* __restrict__ vals, uint32_t sentinel,
                 const uint32_t* __restrict__ split, const uint32_t* __restrict__ pmax,
                 const uint32_t* __restrict__ smin, const uint32_t* __restrict__ tail_list,
-                float* __restrict__ field) {
+                float* __restrict__ field, PeerRows peer) {
   typedef cub::BlockRadixSort<uint32_t, kOwnThreads, kOwnItems, uint32_t> Sort;
   typedef cub::BlockScan<int, kOwnThreads> Scan;
   __shared__ union {
@@ -301,7 +301,10 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
         if (t == 0 && any) {
           const int lr = (int)(lo / (uint32_t)p.W), col = (int)(lo - (uint32_t)lr * (uint32_t)p.W);
           float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
-          *cell = fadd(*cell, s);
+          const float nv = fadd(*cell, s);
+          *cell = nv;
+          if (lr == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;
+          if (lr == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
         }
       }
       continue;
@@ -337,7 +340,10 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
       const uint32_t sk = lo + (key - ch * span);
       const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
       float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
-      *cell = fadd(*cell, s);
+      const float nv = fadd(*cell, s);
+      *cell = nv;
+      if (lr == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;
+      if (lr == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
     }
   }
 }

@@ -44,6 +44,17 @@ struct PFDev {
   float dt, wheel_r, axle;
 };
 
+// Peer-store halo (multi-GPU row strips over NVLink P2P): where this strip's first / last interior
+// row is written, the same value is also stored into the neighbour strip's ghost row, so no halo
+// message is needed. up = the neighbour above's bottom ghost row, dn = the neighbour below's top
+// ghost row (channel 0 of the buffer being written; *_cs = that neighbour's channel stride).
+struct PeerRows {
+  float* up;
+  long long up_cs;
+  float* dn;
+  long long dn_cs;
+};
+
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

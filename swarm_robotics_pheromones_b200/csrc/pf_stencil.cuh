@@ -27,7 +27,14 @@ struct StencilArgs {
   float keep[PF_MAX_CHANNELS];
   float dk[PF_MAX_CHANNELS];
   float del_thr;
+  PeerRows peer;  // neighbour ghost rows of the NEXT buffer (null when not attached)
 };
+
+// per-channel constant without dynamic indexing of the kernel parameter block (which would make
+// the compiler copy the whole struct to local memory)
+__device__ __forceinline__ float pick4(const float (&v)[PF_MAX_CHANNELS], int ch) {
+  return ch == 0 ? v[0] : (ch == 1 ? v[1] : (ch == 2 ? v[2] : v[3]));
+}
 
 template <int ST>
 __device__ __forceinline__ float stencil_cell(float n, float c, float s, float w, float e, float nw,
@@ -92,7 +99,7 @@ __device__ __forceinline__ void row_we(const RowQ& q, int col4, int W, int lane,
 constexpr int kStencilThreads = 256;
 constexpr int kStencilPF = 4;  // rows of loads in flight per thread
 
-template <int ST>
+template <int ST, bool PEER>
 __global__ void __launch_bounds__(kStencilThreads)
 k_stencil_rows(StencilArgs a) {
   const int lane = threadIdx.x & 31;
@@ -103,9 +110,12 @@ k_stencil_rows(StencilArgs a) {
   const int r0 = a.r_begin + blockIdx.y * a.rows_per_cta;
   const int r1 = min(a.r_end, r0 + a.rows_per_cta);
   if (r0 >= r1) return;
-  const float keep = a.keep[ch], dk = a.dk[ch], thr = a.del_thr;
+  const float keep = pick4(a.keep, ch), dk = pick4(a.dk, ch), thr = a.del_thr;
   const float* __restrict__ base = a.cur + ch * a.chan_stride + a.pitch;  // local row 0
   float* __restrict__ obase = a.nxt + ch * a.chan_stride + a.pitch;
+  float* const peer_first = (PEER && r0 == 0 && a.peer.up && live) ? a.peer.up + ch * a.peer.up_cs + col4 : nullptr;
+  float* const peer_last = (PEER && r1 == a.rows && a.peer.dn && live) ? a.peer.dn + ch * a.peer.dn_cs + col4 : nullptr;
+  const int last_row = a.rows - 1;
 
   auto rowp = [&](int r) -> const float* {
     r = max(a.row_lo, min(a.row_hi, r));
@@ -133,6 +143,10 @@ k_stencil_rows(StencilArgs a) {
         row_we(qs, col4, a.W, lane, sw, se);
         float4 o = stencil_vec<ST>(qn.v, qc.v, qs.v, cw, ce, nw, ne, sw, se, keep, dk, thr);
         if (live) *reinterpret_cast<float4*>(obase + (long long)rr * a.pitch + col4) = o;
+        if (PEER) {
+          if (peer_first && rr == 0) *reinterpret_cast<float4*>(peer_first) = o;
+          if (peer_last && rr == last_row) *reinterpret_cast<float4*>(peer_last) = o;
+        }
         qn = qc;
         qc = qs;
         nw = cw; ne = ce;
@@ -158,6 +172,8 @@ k_stencil_scalar(StencilArgs a) {
   const float* pn = base + (long long)rn * a.pitch;
   const float* ps = base + (long long)rs * a.pitch;
   float v = stencil_cell<ST>(pn[col], pc[col], ps[col], pc[jw], pc[je], pn[jw], pn[je], ps[jw],
-                             ps[je], a.keep[ch], a.dk[ch], a.del_thr);
+                             ps[je], pick4(a.keep, ch), pick4(a.dk, ch), a.del_thr);
   a.nxt[ch * a.chan_stride + a.pitch + (long long)r * a.pitch + col] = v;
+  if (r == 0 && a.peer.up) a.peer.up[ch * a.peer.up_cs + col] = v;
+  if (r == a.rows - 1 && a.peer.dn) a.peer.dn[ch * a.peer.dn_cs + col] = v;
 }

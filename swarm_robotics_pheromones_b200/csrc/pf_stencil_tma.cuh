@@ -17,7 +17,7 @@ constexpr int kTmaRowFloats = kTmaCols + 8;   // + 4 halo floats each side
 constexpr int kTmaThreads = kTmaWarps * 32 + 32;  // + producer warp
 
 struct TmaStencilState {
-  bool attr_set[3][4];
+  bool attr_set[3][8];
   char err[256];
 };
 
@@ -57,7 +57,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
-template <int ST, int kStageRows, int kStages>
+// PEER = true only for launches that contain the strip's first / last row while neighbours are attached
+// (the sharded driver launches those two rows on their own), so the streaming instantiation carries
+// no peer logic at all.
+template <int ST, int kStageRows, int kStages, bool PEER>
 __global__ void __launch_bounds__(kTmaThreads)
 k_stencil_tma(StencilArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -116,9 +119,14 @@ k_stencil_tma(StencilArgs a) {
   const int t = threadIdx.x;  // 0..255
   int col4 = c0 + 4 * t;
   const bool live = col4 < a.W;
-  const float keep = a.keep[ch], dk = a.dk[ch], thr = a.del_thr;
+  const float keep = pick4(a.keep, ch), dk = pick4(a.dk, ch), thr = a.del_thr;
   float* __restrict__ obase = a.nxt + ch * a.chan_stride + a.pitch;
   const int my_off = 4 + 4 * t;  // ring offset of this thread's float4 within a row
+  // fused halo (NVLink P2P): only the CTAs that own the strip's first / last row have a peer target;
+  // everything is hoisted into registers so the row loop of all other CTAs is unchanged
+  float* const peer_first = (PEER && r0 == 0 && a.peer.up && live) ? a.peer.up + ch * a.peer.up_cs + col4 : nullptr;
+  float* const peer_last = (PEER && r1 == a.rows && a.peer.dn && live) ? a.peer.dn + ch * a.peer.dn_cs + col4 : nullptr;
+  const int last_row = a.rows - 1;
 
   RowQ qn, qc;
   qn.v = make_float4(0.f, 0.f, 0.f, 0.f); qn.edge = 0.f;
@@ -154,6 +162,10 @@ k_stencil_tma(StencilArgs a) {
           const int rr = r0 + si - 2;
           float4 o = stencil_vec<ST>(qn.v, qc.v, rows[k].v, cw, ce, nw, ne, sw, se, keep, dk, thr);
           if (live) *reinterpret_cast<float4*>(obase + (long long)rr * a.pitch + col4) = o;
+          if (PEER) {
+            if (peer_first && rr == 0) *reinterpret_cast<float4*>(peer_first) = o;
+            if (peer_last && rr == last_row) *reinterpret_cast<float4*>(peer_last) = o;
+          }
         }
         qn = qc; qc = rows[k];
         nw = cw; ne = ce;
@@ -163,19 +175,19 @@ k_stencil_tma(StencilArgs a) {
   }
 }
 
-template <int ST, int R, int S>
+template <int ST, int R, int S, bool PEER>
 static int tma_launch_one(TmaStencilState* st, int slot, const StencilArgs& a, dim3 grid, cudaStream_t s) {
   const size_t smem = (size_t)S * R * kTmaRowFloats * sizeof(float) + 2 * S * sizeof(uint64_t);
   const int sti = ST == 0 ? 0 : (ST == 5 ? 1 : 2);
   if (!st->attr_set[sti][slot]) {
-    cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<ST, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<ST, R, S, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       snprintf(st->err, sizeof(st->err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PF_ECUDA;
     }
     st->attr_set[sti][slot] = true;
   }
-  k_stencil_tma<ST, R, S><<<grid, kTmaThreads, smem, s>>>(a);
+  k_stencil_tma<ST, R, S, PEER><<<grid, kTmaThreads, smem, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(st->err, sizeof(st->err), "launch: %s", cudaGetErrorString(e));
@@ -199,11 +211,17 @@ static int tma_stencil_launch(TmaStencilState* st, int shape, const pf_config& c
   if (rpc > nrows) rpc = nrows;
   a.rows_per_cta = rpc;
   dim3 grid((d.W + kTmaCols - 1) / kTmaCols, (nrows + rpc - 1) / rpc, d.C);
-#define PF_TMA_DISPATCH(R, S, SLOT)                                             \
-  do {                                                                          \
-    if (d.stencil == 0) return tma_launch_one<0, R, S>(st, SLOT, a, grid, s);   \
-    if (d.stencil == 5) return tma_launch_one<5, R, S>(st, SLOT, a, grid, s);   \
-    return tma_launch_one<9, R, S>(st, SLOT, a, grid, s);                       \
+  const bool peer = (a.peer.up && a.r_begin == 0) || (a.peer.dn && a.r_end == a.rows);
+#define PF_TMA_DISPATCH(R, S, SLOT)                                                           \
+  do {                                                                                        \
+    if (peer) {                                                                               \
+      if (d.stencil == 0) return tma_launch_one<0, R, S, true>(st, 4 + SLOT, a, grid, s);     \
+      if (d.stencil == 5) return tma_launch_one<5, R, S, true>(st, 4 + SLOT, a, grid, s);     \
+      return tma_launch_one<9, R, S, true>(st, 4 + SLOT, a, grid, s);                         \
+    }                                                                                         \
+    if (d.stencil == 0) return tma_launch_one<0, R, S, false>(st, SLOT, a, grid, s);          \
+    if (d.stencil == 5) return tma_launch_one<5, R, S, false>(st, SLOT, a, grid, s);          \
+    return tma_launch_one<9, R, S, false>(st, SLOT, a, grid, s);                              \
   } while (0)
   // ring shapes: rows per stage x stages (x 4128 B per row)
   if (shape == 1) PF_TMA_DISPATCH(8, 3, 1);   //  99 KB: 2 CTAs/SM

@@ -66,6 +66,10 @@ struct pf_handle {
   int force_owner_deposit;
   int own_worth;              // host heuristic from the last pf_agents_sort (see there)
   double own_scan_estimate;
+  // peer-store halo (NVLink P2P): neighbours' buffers / flag words, mapped into this process
+  struct PeerLink { float* buf[2]; unsigned int* flags; long long rows, pitch, chan_stride; int set; } peer_up, peer_dn;
+  unsigned int* peer_flags;  // device: [0] written by the strip above, [1] by the strip below
+  unsigned int peer_epoch;
   long long mig_flags_n;   // > 0: scratch holds the migration flags the last move kernel wrote
   const float* mig_flags_x;
   TmaStencilState tma;
@@ -277,6 +281,13 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
   CREATE_CUDA(cudaMalloc(&h->counters, sizeof(unsigned long long) * 16));
   CREATE_CUDA(cudaMemset(h->counters, 0, sizeof(unsigned long long) * 16));
   CREATE_CUDA(cudaMalloc(&h->d_sum, sizeof(double)));
+  {  // peer mailbox block: 256 B of flag words + [2 buffer parities][2 sides][C][pitch] floats. Neighbour strips
+     // store edge rows here (small, IPC-mapped) rather than into the field allocation itself: mapping the
+     // multi-GB field for peer access cost the stencil 40 % (measured), presumably through smaller pages
+    const size_t bytes = 256 + sizeof(float) * 4 * (size_t)cfg->C * h->dev.pitch;
+    CREATE_CUDA(cudaMalloc(&h->peer_flags, bytes));
+    CREATE_CUDA(cudaMemset(h->peer_flags, 0, bytes));
+  }
   {
     int lo = 0, hi = 0;  // the side stream outranks the caller's: its small kernels are not starved
     CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -320,6 +331,7 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->own_tail) cudaFree(h->own_tail);
   if (h->counters) cudaFree(h->counters);
   if (h->d_sum) cudaFree(h->d_sum);
+  if (h->peer_flags) cudaFree(h->peer_flags);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -459,6 +471,27 @@ extern "C" int pf_field_sum_host(pf_handle* h, int channel, double* sum_host, vo
 // ---------------------------------------------------------------------------------------------
 // K1 launch
 // ---------------------------------------------------------------------------------------------
+// neighbour ghost rows of physical buffer `k` (see PeerRows)
+// this strip's mailbox for buffer parity k: side 0 = rows arriving from the strip above, side 1 = from below
+static float* mailbox_of(unsigned int* flags_base, int k, int C, long long pitch) {
+  return (float*)((char*)flags_base + 256) + (size_t)k * 2 * C * pitch;
+}
+
+// where this strip's edge rows of physical buffer `k` go in the neighbours' mailboxes (see PeerRows)
+static PeerRows peer_rows(const pf_handle* h, int k) {
+  PeerRows r;
+  r.up = nullptr; r.dn = nullptr; r.up_cs = 0; r.dn_cs = 0;
+  if (h->peer_up.set) {  // the strip above receives it as "from below" (side 1)
+    r.up = h->peer_up.buf[k] + (size_t)h->cfg.C * h->peer_up.pitch;
+    r.up_cs = h->peer_up.pitch;
+  }
+  if (h->peer_dn.set) {  // the strip below receives it as "from above" (side 0)
+    r.dn = h->peer_dn.buf[k];
+    r.dn_cs = h->peer_dn.pitch;
+  }
+  return r;
+}
+
 static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) {
   if (r_begin >= r_end) return PF_OK;
   const PFDev& d = h->dev;
@@ -471,6 +504,7 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) 
   a.row_hi = (h->cfg.row1 == h->cfg.H) ? d.rows - 1 : d.rows;
   for (int k = 0; k < PF_MAX_CHANNELS; ++k) { a.keep[k] = d.keep[k]; a.dk[k] = d.dk[k]; }
   a.del_thr = d.del_thr;
+  a.peer = peer_rows(h, h->cur ^ 1);
   const int nrows = r_end - r_begin;
   if (d.W % 4 != 0) {
     dim3 grid(blocks_for(d.W, 256), nrows, d.C);
@@ -504,9 +538,16 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) 
   }
   a.rows_per_cta = rpc;
   dim3 grid(xblocks, (nrows + rpc - 1) / rpc, d.C);
-  if (d.stencil == 0) k_stencil_rows<0><<<grid, kStencilThreads, 0, s>>>(a);
-  else if (d.stencil == 5) k_stencil_rows<5><<<grid, kStencilThreads, 0, s>>>(a);
-  else k_stencil_rows<9><<<grid, kStencilThreads, 0, s>>>(a);
+  const bool peer = (a.peer.up && a.r_begin == 0) || (a.peer.dn && a.r_end == a.rows);
+  if (peer) {
+    if (d.stencil == 0) k_stencil_rows<0, true><<<grid, kStencilThreads, 0, s>>>(a);
+    else if (d.stencil == 5) k_stencil_rows<5, true><<<grid, kStencilThreads, 0, s>>>(a);
+    else k_stencil_rows<9, true><<<grid, kStencilThreads, 0, s>>>(a);
+  } else {
+    if (d.stencil == 0) k_stencil_rows<0, false><<<grid, kStencilThreads, 0, s>>>(a);
+    else if (d.stencil == 5) k_stencil_rows<5, false><<<grid, kStencilThreads, 0, s>>>(a);
+    else k_stencil_rows<9, false><<<grid, kStencilThreads, 0, s>>>(a);
+  }
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -574,7 +615,7 @@ static int owner_sum(pf_handle* h, long long n, cudaStream_t s) {
   PF_LAUNCH_CHECK(h);
   k_deposit_owner<<<nchunks, kOwnThreads, 0, s>>>(h->dev, n, nchunks, h->own_body, keys_in, vals_in, h->sentinel,
                                                   h->own_split, h->own_pmax, h->own_smin, h->own_tail,
-                                                  h->buf[h->cur]);
+                                                  h->buf[h->cur], peer_rows(h, h->cur));
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -589,7 +630,7 @@ static int sort_and_sum(pf_handle* h, long long n, cudaStream_t s) {
   PF_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_temp, bytes, keys_in, keys_out, vals_in, vals_out,
                                              (int)n, 0, h->key_bits, s));
   k_deposit_segsum<<<blocks_for(n, 256), 256, 0, s>>>(h->dev, n, keys_out, vals_out, h->sentinel,
-                                                     h->buf[h->cur]);
+                                                     h->buf[h->cur], peer_rows(h, h->cur));
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -1044,6 +1085,97 @@ extern "C" int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32
   PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
   k_migrate_fill<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, flags, ranks, buf, buf2, cap, a->x, a->y, a->theta,
                                                       a->wl, a->wr, a->meta, a->gid, h->counters, body);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer-store halo (NVLink P2P)
+// ---------------------------------------------------------------------------------------------
+extern "C" int pf_peer_export(pf_handle* h, pf_peer_info* out) {
+  if (!h || !out) return PF_EINVAL;
+  out->buf0 = mailbox_of(h->peer_flags, 0, h->cfg.C, h->dev.pitch);
+  out->buf1 = mailbox_of(h->peer_flags, 1, h->cfg.C, h->dev.pitch);
+  out->flags = h->peer_flags;
+  out->rows = h->dev.rows; out->pitch = h->dev.pitch; out->chan_stride = h->dev.chan_stride;
+  return PF_OK;
+}
+
+extern "C" int pf_peer_ipc_handles(pf_handle* h, uint8_t* out192) {
+  if (!h || !out192) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memset(out192, 0, 192);
+  cudaIpcMemHandle_t mh;  // one small allocation: flag words + mailboxes (the field itself is never exported)
+  PF_CUDA(h, cudaIpcGetMemHandle(&mh, h->peer_flags));
+  memcpy(out192, &mh, 64);
+  return PF_OK;
+}
+
+// map a neighbour process's buffers into this process; `dims` = that neighbour's pf_peer_export
+extern "C" int pf_peer_ipc_open(pf_handle* h, const uint8_t* in192, const pf_peer_info* dims, pf_peer_info* out) {
+  if (!h || !in192 || !dims || !out) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  void* base = nullptr;
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, in192, 64);
+  PF_CUDA(h, cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+  *out = *dims;
+  out->flags = base;
+  out->buf0 = mailbox_of((unsigned int*)base, 0, h->cfg.C, dims->pitch);
+  out->buf1 = mailbox_of((unsigned int*)base, 1, h->cfg.C, dims->pitch);
+  return PF_OK;
+}
+
+extern "C" int pf_peer_attach(pf_handle* h, const pf_peer_info* up, const pf_peer_info* down) {
+  if (!h) return PF_EINVAL;
+  if ((up && h->cfg.row0 == 0) || (down && h->cfg.row1 == h->cfg.H))
+    return set_err(h, PF_EINVAL, "pf_peer_attach: no neighbour on that side of this strip");
+  auto set = [](pf_handle::PeerLink& l, const pf_peer_info* i) {
+    memset(&l, 0, sizeof(l));
+    if (!i) return;
+    l.buf[0] = (float*)i->buf0; l.buf[1] = (float*)i->buf1; l.flags = (unsigned int*)i->flags;
+    l.rows = i->rows; l.pitch = i->pitch; l.chan_stride = i->chan_stride; l.set = 1;
+  };
+  set(h->peer_up, up);
+  set(h->peer_dn, down);
+  graph_drop(h);
+  return PF_OK;
+}
+
+extern "C" int pf_peer_push_edges(pf_handle* h, void* stream) {
+  if (!h) return PF_EINVAL;
+  if (!h->peer_up.set && !h->peer_dn.set) return PF_OK;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  dim3 grid(blocks_for(h->cfg.W, 256), h->cfg.C);
+  k_peer_push_edges<<<grid, 256, 0, (cudaStream_t)stream>>>(h->dev, h->buf[h->cur], peer_rows(h, h->cur));
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+extern "C" int pf_peer_signal(pf_handle* h, void* stream) {
+  if (!h) return PF_EINVAL;
+  h->peer_epoch += 1;
+  if (!h->peer_up.set && !h->peer_dn.set) return PF_OK;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_peer_signal<<<1, 1, 0, (cudaStream_t)stream>>>(h->peer_up.set ? h->peer_up.flags + 1 : nullptr,
+                                                  h->peer_dn.set ? h->peer_dn.flags + 0 : nullptr, h->peer_epoch);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+extern "C" int pf_peer_wait(pf_handle* h, void* stream) {
+  if (!h) return PF_EINVAL;
+  if (!h->peer_up.set && !h->peer_dn.set) return PF_OK;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_peer_wait<<<1, 1, 0, (cudaStream_t)stream>>>(h->peer_up.set ? h->peer_flags + 0 : nullptr,
+                                                h->peer_dn.set ? h->peer_flags + 1 : nullptr, h->peer_epoch);
+  PF_LAUNCH_CHECK(h);
+  // mailbox of the current buffer -> this strip's ghost rows
+  dim3 grid(blocks_for(h->cfg.W, 256), h->cfg.C);
+  k_mailbox_to_ghosts<<<grid, 256, 0, (cudaStream_t)stream>>>(h->dev, h->buf[h->cur],
+                                                            mailbox_of(h->peer_flags, h->cur, h->cfg.C, h->dev.pitch),
+                                                            h->peer_up.set, h->peer_dn.set);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }

@@ -249,6 +249,37 @@ class PheroField:
         self._ck(self._L.pf_migrate_unpack2(self._h, C.byref(a.struct()), _ptr(buf), _ptr(buf2), cap,
                                             self._s()))
 
+    # -- peer-store halo (NVLink P2P)
+    def peer_export(self) -> abi.PFPeerInfo:
+        info = abi.PFPeerInfo()
+        self._ck(self._L.pf_peer_export(self._h, C.byref(info)))
+        return info
+
+    def peer_ipc_handles(self) -> bytes:
+        buf = (C.c_uint8 * 192)()
+        self._ck(self._L.pf_peer_ipc_handles(self._h, buf))
+        return bytes(buf)
+
+    def peer_ipc_open(self, handles: bytes, dims: abi.PFPeerInfo) -> abi.PFPeerInfo:
+        src = (C.c_uint8 * 192).from_buffer_copy(handles)
+        out = abi.PFPeerInfo()
+        self._ck(self._L.pf_peer_ipc_open(self._h, src, C.byref(dims), C.byref(out)))
+        return out
+
+    def peer_attach(self, up: Optional[abi.PFPeerInfo], down: Optional[abi.PFPeerInfo]):
+        self._ck(self._L.pf_peer_attach(self._h, C.byref(up) if up is not None else None,
+                                        C.byref(down) if down is not None else None))
+        self._peer_keep = (up, down)
+
+    def peer_push_edges(self):
+        self._ck(self._L.pf_peer_push_edges(self._h, self._s()))
+
+    def peer_signal(self):
+        self._ck(self._L.pf_peer_signal(self._h, self._s()))
+
+    def peer_wait(self):
+        self._ck(self._L.pf_peer_wait(self._h, self._s()))
+
     # -- counters / tuning
     def counters(self) -> abi.PFCounters:
         c = abi.PFCounters()

@@ -121,6 +121,46 @@ class CudaStrip:
     def synchronize(self):
         torch.cuda.synchronize(self.field.device)
 
+    # ---- peer-store halo (NVLink P2P): the halo exchange fused into the deposit / stencil kernels
+    peer = False
+
+    def peer_attach_local(self, up: Optional["CudaStrip"], down: Optional["CudaStrip"]):
+        """neighbour strips living in this process on the same device: raw pointers"""
+        self.field.peer_attach(up.field.peer_export() if up is not None else None,
+                               down.field.peer_export() if down is not None else None)
+        self.peer = True
+
+    def peer_attach_ipc(self, rank: int, world: int, group=None):
+        """one process per GPU: exchange CUDA IPC handles of the field buffers and the flag words with
+        the two neighbour ranks and map them (cudaIpcOpenMemHandle enables NVLink peer access)"""
+        import torch.distributed as dist
+        info = self.field.peer_export()
+        mine = (self.field.peer_ipc_handles(), int(info.rows), int(info.pitch), int(info.chan_stride))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+
+        def opened(r):
+            if r < 0 or r >= world:
+                return None
+            handles, rows, pitch, cs = everyone[r]
+            dims = abi.PFPeerInfo()
+            dims.rows, dims.pitch, dims.chan_stride = rows, pitch, cs
+            return self.field.peer_ipc_open(handles, dims)
+
+        self.field.peer_attach(opened(rank - 1), opened(rank + 1))
+        self.peer = True
+
+    def peer_prime(self):
+        """make the neighbours' ghost rows of the current buffer valid (initial state / after uploads)"""
+        self.field.peer_push_edges()
+        self.field.peer_signal()
+
+    def peer_signal(self):
+        self.field.peer_signal()
+
+    def peer_wait(self):
+        self.field.peer_wait()
+
 
 class StripWorker:
     """Phase logic of one rank, independent of how bytes move between ranks."""
@@ -230,12 +270,31 @@ class LocalDriver:
                 for d, s in zip(tensors, src):
                     d.copy_(s)
 
+    def attach_peers(self):
+        """fuse the halo into the kernels: every strip stores its edge rows straight into its
+        neighbours' ghost rows (all strips of this driver live on one device)"""
+        for i, w in enumerate(self.w):
+            w.b.peer_attach_local(self.w[i - 1].b if i > 0 else None,
+                                  self.w[i + 1].b if i + 1 < len(self.w) else None)
+        for w in self.w:
+            w.b.peer_prime()
+        for w in self.w:
+            w.b.peer_wait()
+        self.peer = True
+
+    peer = False
+
     def tick(self, sense_enabled: bool = True):
         for w in self.w:
             w.deposit(sense_enabled)
-        self._move(self.w, lambda w: w.halo_sends(), lambda w: w.halo_recvs())
+            if self.peer:
+                w.b.peer_signal()
+        if not self.peer:
+            self._move(self.w, lambda w: w.halo_sends(), lambda w: w.halo_recvs())
         for w in self.w:
             w.field_interior_a()
+            if self.peer:
+                w.b.peer_wait()
             w.agents(sense_enabled)
             w.pack()
         self._move(self.w, lambda w: w.migrate_sends(), lambda w: w.migrate_recvs())
@@ -303,6 +362,32 @@ class DistDriver:
         mark("start")
         w.deposit(sense_enabled)
         mark("deposit")
+        if getattr(w.b, "peer", False):
+            # halo fused into the kernels (NVLink P2P stores): only an epoch flag crosses between ranks
+            main = torch.cuda.current_stream()
+            w.b.peer_signal()
+            w.field_interior_a()
+            mark("stencil_a")
+            w.b.peer_wait()
+            mark("wait_halo")
+            w.agents(sense_enabled, move)
+            mark("agents")
+            if move:
+                w.pack()
+                mark("pack")
+                self._comm(w.migrate_sends(), w.migrate_recvs(), self.ev_pack, self.ev_mig)
+            w.field_rest()
+            mark("stencil_b+edges")
+            if move:
+                main.wait_event(self.ev_mig)
+                mark("wait_migration")
+                w.unpack()
+                mark("unpack")
+            else:
+                w.ticks += 1
+            if marks is not None:
+                self._marks.append(marks)
+            return
         if self.overlap:
             main = torch.cuda.current_stream()
             self._comm(w.halo_sends(), w.halo_recvs(), self.ev_ready, self.ev_done)

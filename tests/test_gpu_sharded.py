@@ -12,9 +12,10 @@ from tests.test_sharded_cpu import _scenario
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("peer", [False, True])
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("variant", [1, 2])
-def test_strips_equal_unsharded_bitexact(world, variant):
+def test_strips_equal_unsharded_bitexact(world, variant, peer):
     cfg, x, y, th, st = _scenario(seed=11, n=6000, H=128, W=256, C=2)
     nticks = 150
     o = dense.DenseOracle(cfg)
@@ -30,6 +31,8 @@ def test_strips_equal_unsharded_bitexact(world, variant):
         strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)  # small dense test arena
         workers.append(sharded.StripWorker(strip, r, world))
     drv = sharded.LocalDriver(workers)
+    if peer:  # halo fused into the deposit / stencil kernels (peer stores into the neighbours' ghosts)
+        drv.attach_peers()
     for t in range(nticks):
         if t % 16 == 0:  # re-order by cell: switches the strips' deposit to the owner-computes kernel,
             for w in workers:  # arrivals then live in the tail chunks until the next sort

@@ -23,6 +23,7 @@ ap.add_argument("--grid", type=int, default=2048)
 ap.add_argument("--agents", type=int, default=200000)
 ap.add_argument("--no-overlap", action="store_true")
 ap.add_argument("--sort-every", type=int, default=16)
+ap.add_argument("--peer", action="store_true", help="peer-store halo (CUDA IPC + NVLink P2P) instead of NCCL")
 args = ap.parse_args()
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -53,6 +54,11 @@ scfg = sharded.strip_config(cfg, world, rank, device=local)
 strip = sharded.CudaStrip(scfg, p["x"], p["y"], p["theta"], p["state"], p["gid"],
                           capacity=int(len(p["x"]) * 1.5) + 1024, migrate_cap=8192)
 drv = sharded.DistDriver(sharded.StripWorker(strip, rank, world), overlap=not args.no_overlap)
+if args.peer:
+    strip.peer_attach_ipc(rank, world)
+    dist.barrier()
+    strip.peer_prime()
+    strip.peer_wait()
 for t in range(args.ticks):
     if args.sort_every and t % args.sort_every == 0:
         strip.sort_agents()
@@ -96,7 +102,7 @@ if rank == 0:
         for k, f in enumerate(("x", "y", "theta", "wl", "wr", "meta")))
     mig = strip.field.counters()
     ok = same_field and same_agents
-    print(f"dist_parity world={world} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
+    print(f"dist_parity world={world} peer_halo={args.peer} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
           f"agents_bitexact={same_agents} (rank0 migrated_out={mig.migrated_out}, dropped={mig.migrate_dropped}) "
           f"-> {'PASS' if ok else 'FAIL'}", flush=True)
 else:
