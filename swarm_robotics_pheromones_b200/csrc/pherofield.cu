@@ -10,6 +10,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -274,6 +275,12 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
     }                                                                                      \
   } while (0)
   CREATE_CUDA(cudaSetDevice(cfg->device));
+  {  // L2 fetch granularity: the agent kernels touch 4 B per 32 B sector at random; the default 64 B
+     // granularity doubles their DRAM traffic. PF_L2_FETCH=32|64|128 overrides (device-wide limit).
+    const char* e = getenv("PF_L2_FETCH");
+    if (e && *e) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+    cudaGetLastError();
+  }
   CREATE_CUDA(cudaMalloc(&h->buf[0], sizeof(float) * h->buf_elems));
   CREATE_CUDA(cudaMalloc(&h->buf[1], sizeof(float) * h->buf_elems));
   CREATE_CUDA(cudaMemset(h->buf[0], 0, sizeof(float) * h->buf_elems));
