@@ -137,7 +137,7 @@ __global__ void k_owner_splitters(const uint32_t* __restrict__ sorted_keys, long
   split[b] = v;
 }
 
-__global__ void __launch_bounds__(kOwnThreads)
+__global__ void __launch_bounds__(kOwnThreads, 4)
 k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict__ body_chunks,
                 const uint32_t* __restrict__ keys, const float* __restrict__ vals, uint32_t sentinel,
                 const uint32_t* __restrict__ split, const uint32_t* __restrict__ pmax,
@@ -154,6 +154,7 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
   __shared__ uint32_t st_lo[34], st_hi[34];
   __shared__ int st_n;
   __shared__ int tcand[kOwnThreads];  // tail chunks whose bounds meet the current key range
+  __shared__ int jrange[2];
 
   const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
   const int b = blockIdx.x;
@@ -172,16 +173,29 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
     const uint32_t lo = st_lo[st_n - 1], hi = st_hi[st_n - 1];
     __syncthreads();
     if (t == 0) st_n -= 1;
-    // candidate chunks: first j with pmax[j] >= lo ... last j with smin[j] < hi
-    int j0, j1;
-    {
-      int a = 0, z = nchunks;  // lower bound of pmax >= lo
-      while (a < z) { int m = (a + z) >> 1; if (pmax[m] >= lo) z = m; else a = m + 1; }
-      j0 = a;
-      a = 0; z = nchunks;      // first j with smin[j] >= hi  -> j1 = that - 1
-      while (a < z) { int m = (a + z) >> 1; if (smin[m] >= hi) z = m; else a = m + 1; }
-      j1 = a - 1;
+    // candidate chunks: first j with pmax[j] >= lo ... last j with smin[j] < hi. A 32-ary search by
+    // one warp each (two dependent load rounds for 16 K chunks instead of fourteen) run side by side.
+    if (t < 64) {
+      const int w = t >> 5, l = t & 31;
+      const uint32_t* arr = w == 0 ? pmax : smin;
+      const uint32_t bound = w == 0 ? lo : hi;
+      int a = 0, z = nchunks;  // invariant: answer (first index with arr[idx] >= bound) lies in [a, z]
+      while (z - a > 0) {
+        const int step = (z - a + 31) / 32;
+        const int idx = a + l * step;           // probe 32 equally spaced positions
+        const bool ge = idx < z ? (arr[idx] >= bound) : true;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (m == 0u) { a = a + 31 * step + 1; continue; }  // every probe below the bound
+        const int first = __ffs(m) - 1;         // first probe that is >= bound (probes at idx >= z count)
+        const int na = first == 0 ? a : a + (first - 1) * step + 1;
+        const int nz = min(z, a + first * step);
+        if (first == 0) { z = a; break; }
+        a = na; z = nz;
+      }
+      if (l == 0) jrange[w] = z;
     }
+    __syncthreads();
+    const int j0 = jrange[0], j1 = jrange[1] - 1;
     __syncthreads();
     const uint32_t span = hi - lo;
     int count = 0;
@@ -331,19 +345,46 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
       lv[e] = sv8[q];
     }
     __syncthreads();
-    for (int e = t; e < count; e += kOwnThreads) {
-      const uint32_t key = lk[e];
-      if (e > 0 && lk[e - 1] == key) continue;  // not a segment head
-      float s = __uint_as_float(lv[e]);
-      for (int f = e + 1; f < count && lk[f] == key; ++f) s = fadd(s, __uint_as_float(lv[f]));
-      const uint32_t ch = key / span;
-      const uint32_t sk = lo + (key - ch * span);
-      const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
-      float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
-      const float nv = fadd(*cell, s);
-      *cell = nv;
-      if (lr == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;
-      if (lr == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
+    // read-modify-write of the touched cells: every thread owns up to kOwnItems segment heads; all
+    // their cell loads are issued first (distinct cells: one writer each), then the adds and stores
+    constexpr int kBatch = 4;
+    for (int q0 = 0; q0 < kOwnItems; q0 += kBatch) {
+      float* cellp[kBatch];
+      float ssum[kBatch], cval[kBatch];
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        const int e = t + (q0 + q) * kOwnThreads;
+        cellp[q] = nullptr;
+        if (e < count) {
+          const uint32_t key = lk[e];
+          if (e == 0 || lk[e - 1] != key) {  // segment head
+            float s = __uint_as_float(lv[e]);
+            for (int f = e + 1; f < count && lk[f] == key; ++f) s = fadd(s, __uint_as_float(lv[f]));
+            const uint32_t ch = key / span;
+            const uint32_t sk = lo + (key - ch * span);
+            const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
+            cellp[q] = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
+            ssum[q] = s;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q)
+        if (cellp[q]) cval[q] = __ldcg(cellp[q]);
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q)
+        if (cellp[q]) {
+          const float nv = fadd(cval[q], ssum[q]);
+          *cellp[q] = nv;
+          if (peer.up || peer.dn) {  // strips only: mirror edge-row cells into the neighbour's mailbox
+            const uint32_t key = lk[t + (q0 + q) * kOwnThreads];
+            const uint32_t ch = key / span;
+            const uint32_t sk = lo + (key - ch * span);
+            const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
+            if (lr == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;
+            if (lr == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
+          }
+        }
     }
   }
 }
