@@ -319,6 +319,11 @@ int pf_counters_reset(pf_handle* h, void* stream);
 /* number of kernels this handle has launched (bench.py reports it as gpu_launches) */
 int pf_launch_count(const pf_handle* h, uint64_t* n);
 
+/* pf_step diagnostics: ticks whose stencil was handed the next tick's deposits, and how many of
+ * those fell back on the device to the separate deposit kernels (a tile too crowded).
+ * Synchronises the device. */
+int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_back);
+
 /* Per-phase device times of pf_step, from CUDA events recorded on the launching streams while
  * profiling is enabled (bench.py's live roofline numbers). Times are sums over `ticks` ticks. */
 typedef struct pf_profile {
@@ -387,6 +392,9 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
 #define PF_OPT_NO_OWNER_DEPOSIT 4 /* always use the global radix sort for the agent deposit */
 #define PF_OPT_FORCE_OWNER_DEPOSIT 5 /* use the sort-free deposit after pf_agents_sort even where the
                                         density heuristic prefers the radix sort (dense clusters) */
+#define PF_OPT_NO_TILE_DEPOSIT 6 /* pf_step: never hand the next tick's deposits to the stencil kernel
+                                   (default: done where the sort-free deposit is in use and the TMA
+                                   stencil runs; falls back on the device when a tile is too crowded) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */
 int pf_set_option(pf_handle* h, int option, int value);

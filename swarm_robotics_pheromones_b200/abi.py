@@ -35,6 +35,7 @@ OPT_NO_FUSED_KEYS = 2
 OPT_USE_GRAPH = 3
 OPT_NO_OWNER_DEPOSIT = 4
 OPT_FORCE_OWNER_DEPOSIT = 5
+OPT_NO_TILE_DEPOSIT = 6
 STEP_DEPOSIT, STEP_SENSE, STEP_FIELD, STEP_MOVE, STEP_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 
 # reference constants --------------------------------------------------------------------------

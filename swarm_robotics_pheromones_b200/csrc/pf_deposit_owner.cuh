@@ -10,8 +10,8 @@
 //      hold a key in [lo, hi)" is a contiguous, binary-searchable chunk range — a guaranteed
 //      superset, however far agents have drifted;
 //   3. k_deposit_owner: each CTA scans its candidate chunks (L2-resident re-reads), compacts the
-//      agents that fall into its key range in ARRAY ORDER, block-radix-sorts them by cell (stable),
-//      sums each cell's amounts in that order and adds the total to the field — one writer per cell,
+//      agents that fall into its key range in ARRAY ORDER, groups them by cell in a shared-memory
+//      hash table, sums each cell's amounts in that order and adds the total to the field — one writer per cell,
 //      no atomics on the field, same summation order as the global-sort path and the oracle.
 //      Ranges holding more than kOwnCap agents are bisected (work stack); a single cell holding more
 //      than kOwnCap agents is summed sequentially.
@@ -24,7 +24,10 @@
 constexpr int kOwnChunk = 1024;
 constexpr int kOwnThreads = 256;
 constexpr int kOwnItems = 8;
-constexpr int kOwnCap = kOwnThreads * kOwnItems;  // 2048 agents per sort
+constexpr int kOwnCap = kOwnThreads * kOwnItems;  // 2048 agents per pass
+constexpr int kOwnSlotBits = 12;
+constexpr int kOwnSlots = 1 << kOwnSlotBits;  // hash slots: load factor <= 0.5
+constexpr int kOwnShared = 512;               // short list of agents sharing a cell; longer -> full scan
 
 // record the per-chunk key bounds (called by every thread of a warp whose lanes cover consecutive
 // agents of ONE chunk; `sk` = sort key, or 0xffffffff when the agent does not deposit)
@@ -49,10 +52,18 @@ __device__ __forceinline__ void owner_note_bounds(uint32_t* __restrict__ cmin, u
 __global__ void __launch_bounds__(1024)
 k_owner_bounds(int all_chunks, uint32_t* __restrict__ body_chunks, uint32_t* __restrict__ cmin,
                uint32_t* __restrict__ cmax, uint32_t* __restrict__ pmax, uint32_t* __restrict__ smin,
-               uint32_t* __restrict__ tail_list) {
+               uint32_t* __restrict__ tail_list, uint32_t* __restrict__ only_if) {
   typedef cub::BlockScan<uint32_t, 1024> Scan;
   __shared__ typename Scan::TempStorage tmp;
   __shared__ uint32_t carry;
+  if (only_if && *only_if == 0u) {  // deposits already applied by the stencil: only reset the bounds
+    for (int j = threadIdx.x; j < all_chunks; j += 1024) {
+      cmin[j] = 0xffffffffu;
+      cmax[j] = 0u;
+    }
+    return;
+  }
+  if (only_if && threadIdx.x == 0) only_if[1] += 1u;  // ticks whose fused deposit fell back (one CTA)
   const int nchunks = min((int)*body_chunks, all_chunks);
   if (threadIdx.x == 0) carry = 0u;
   __syncthreads();
@@ -137,29 +148,232 @@ __global__ void k_owner_splitters(const uint32_t* __restrict__ sorted_keys, long
   split[b] = v;
 }
 
+// channel of a cell key without an integer division (C <= PF_MAX_CHANNELS = 4)
+__device__ __forceinline__ uint32_t owner_channel(uint32_t key, uint32_t plane) {
+  const unsigned long long k = key, pl = plane;  // 3 * plane may not fit 32 bits
+  return (k >= pl ? 1u : 0u) + (k >= 2ull * pl ? 1u : 0u) + (k >= 3ull * pl ? 1u : 0u);
+}
+
+typedef cub::BlockRadixSort<unsigned long long, kOwnThreads, kOwnItems, uint32_t> OwnSort;
+struct OwnHash {
+  uint32_t ht[kOwnSlots];         // cell -> index into lk[] of the agent that claimed the slot
+  uint32_t coll[kOwnSlots / 32];  // slot holds more than one agent
+  uint16_t clist[kOwnShared];     // indices of all agents of shared cells
+};
+union OwnScratch {
+  OwnHash h;
+  typename OwnSort::TempStorage sort;  // crowded ranges only
+};
+
+// Hash phase shared by the deposit kernels. lk[0..count) = cell keys (any order). Each key claims one
+// slot of the shared-memory hash table; a collision bit says whether any other agent shares the
+// cell. All agents of shared cells go on the short list u->h.clist (*ncl entries; more than
+// kOwnShared means "crowded": the list is then incomplete). Returns this thread's mask of items
+// (e = t + q * kOwnThreads) that sit in shared cells. The caller has cleared ht / coll / *ncl and
+// synchronised; ends with a barrier.
+__device__ __forceinline__ unsigned owner_hash_build(int count, const uint32_t* lk, OwnScratch* u, int* ncl) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < kOwnItems; ++q) {
+    const int e = t + q * kOwnThreads;
+    if (e < count) {
+      const uint32_t key = lk[e];
+      uint32_t slot = (key * 2654435761u) >> (32 - kOwnSlotBits);
+      while (true) {
+        const uint32_t old = atomicCAS(&u->h.ht[slot], 0xffffffffu, (uint32_t)e);
+        if (old == 0xffffffffu) break;
+        if (lk[old] == key) {  // the slot belongs to this cell already
+          atomicOr(&u->h.coll[slot >> 5], 1u << (slot & 31u));
+          break;
+        }
+        slot = (slot + 1u) & (kOwnSlots - 1);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned shared8 = 0u;
+#pragma unroll
+  for (int q = 0; q < kOwnItems; ++q) {
+    const int e = t + q * kOwnThreads;
+    if (e < count) {
+      const uint32_t key = lk[e];
+      uint32_t slot = (key * 2654435761u) >> (32 - kOwnSlotBits);
+      while (lk[u->h.ht[slot]] != key) slot = (slot + 1u) & (kOwnSlots - 1);  // find the cell's slot again
+      if ((u->h.coll[slot >> 5] >> (slot & 31u)) & 1u) {
+        shared8 |= 1u << q;
+        const int pos = atomicAdd(ncl, 1);
+        if (pos < kOwnShared) u->h.clist[pos] = (uint16_t)e;
+      }
+    }
+  }
+  __syncthreads();
+  return shared8;
+}
+
+// Item e sits in a shared cell: is it the cell's head (smallest array index)? If so, *s (preset to
+// its own amount) becomes the cell's amounts summed in array order — the summation order of the
+// global-sort path and of the oracle. nshared <= kOwnShared.
+__device__ __forceinline__ bool owner_shared_sum(int e, int nshared, const uint32_t* lk, const uint32_t* lv,
+                                                 const uint32_t* le, const OwnScratch* u, float* s) {
+  const uint32_t key = lk[e], mine = le[e];
+  for (int i = 0; i < nshared; ++i) {
+    const int c = (int)u->h.clist[i];
+    if (lk[c] == key && le[c] < mine) return false;
+  }
+  uint32_t last = mine;  // next larger array index with this cell, until there is none
+  while (true) {
+    uint32_t best = 0xffffffffu;
+    int bi = -1;
+    for (int i = 0; i < nshared; ++i) {
+      const int c = (int)u->h.clist[i];
+      const uint32_t ec = le[c];
+      if (lk[c] == key && ec > last && ec < best) { best = ec; bi = c; }
+    }
+    if (bi < 0) break;
+    *s = fadd(*s, __uint_as_float(lv[bi]));
+    last = best;
+  }
+  return true;
+}
+
+// Group `count` (0 < count <= kOwnCap) selected agents by cell and add each cell's ordered sum to the
+// field. lk = keys local to [lo, lo + span) (channel * span + cell - lo), lv = amounts, le = array
+// indices, in any order. The caller has cleared u->h.ht / u->h.coll and *ncl, and synchronised.
+// A cell with one depositor (almost all of them at bench densities) is updated directly.
+__device__ __forceinline__ void owner_group_add(const PFDev& p, uint32_t lo, uint32_t span, int count,
+                                                uint32_t* lk, uint32_t* lv, const uint32_t* le,
+                                                OwnScratch* u, int* ncl, float* __restrict__ field,
+                                                const PeerRows& peer) {
+  const int t = threadIdx.x;
+  const bool use_red = p.dep_red && !peer.up && !peer.dn;  // mirrored edge rows need the new value
+  const unsigned shared8 = owner_hash_build(count, lk, u, ncl);
+    const int nshared = *ncl;
+
+    if (nshared > kOwnShared) {
+      // crowded range: stable order by (cell, array index) from one block radix sort of the
+      // composite key, then every segment head sums its run
+      __syncthreads();
+      unsigned long long ck8[kOwnItems];
+      uint32_t sv8[kOwnItems];
+#pragma unroll
+      for (int q = 0; q < kOwnItems; ++q) {
+        const int e = t * kOwnItems + q;
+        ck8[q] = e < count ? (((unsigned long long)lk[e] << 32) | le[e]) : ~0ull;
+        sv8[q] = e < count ? lv[e] : 0u;
+      }
+      __syncthreads();
+      const unsigned long long maxkey = (unsigned long long)p.C * span;  // one past the largest local key
+      int end_bit = 1;
+      while ((1ull << end_bit) <= maxkey && end_bit < 32) ++end_bit;  // all-ones padding sorts last
+      OwnSort(u->sort).Sort(ck8, sv8, 0, 32 + end_bit);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kOwnItems; ++q) {
+        const int e = t * kOwnItems + q;
+        lk[e] = (uint32_t)(ck8[q] >> 32);
+        lv[e] = sv8[q];
+      }
+      __syncthreads();
+      for (int q = 0; q < kOwnItems; ++q) {
+        const int e = t + q * kOwnThreads;
+        if (e >= count) break;
+        const uint32_t key = lk[e];
+        if (e != 0 && lk[e - 1] == key) continue;  // not a segment head
+        float s = __uint_as_float(lv[e]);
+        for (int f = e + 1; f < count && lk[f] == key; ++f) s = fadd(s, __uint_as_float(lv[f]));
+        const uint32_t ch = key / span;
+        const uint32_t sk = lo + (key - ch * span);
+        const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
+        float* cell = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
+        const float nv = fadd(__ldcg(cell), s);
+        *cell = nv;
+        if (lr == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;
+        if (lr == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
+      }
+      return;
+    }
+
+    // read-modify-write of the touched cells: one writer per cell; the cell loads of a batch are
+    // issued before its adds and stores
+    constexpr int kBatch = 4;
+#pragma unroll
+    for (int q0 = 0; q0 < kOwnItems; q0 += kBatch) {
+      float* cellp[kBatch];
+      float ssum[kBatch], cval[kBatch];
+      int erow[kBatch];
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        const int e = t + (q0 + q) * kOwnThreads;
+        cellp[q] = nullptr;
+        if (e < count) {
+          const uint32_t key = lk[e];
+          float s = __uint_as_float(lv[e]);
+          bool head = true;
+          if ((shared8 >> (q0 + q)) & 1u) head = owner_shared_sum(e, nshared, lk, lv, le, u, &s);
+          if (head) {
+            const uint32_t ch = key / span;
+            const uint32_t sk = lo + (key - ch * span);
+            const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
+            cellp[q] = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
+            ssum[q] = s;
+            erow[q] = lr;
+          }
+        }
+      }
+      if (use_red) {
+        // one writer per cell and kernel, so a reduction performed by the L2 (no round trip to the
+        // SM, no partially written sector) rounds exactly like the load-add-store below. The L2
+        // flushes subnormal operands; with every amount >= 1e-30 (p.dep_red) a subnormal cell
+        // value is below half an ulp of the sum either way.
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
+          if (cellp[q]) atomicAdd(cellp[q], ssum[q]);
+        continue;
+      }
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q)
+        if (cellp[q]) cval[q] = __ldcg(cellp[q]);
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q)
+        if (cellp[q]) {
+          const float nv = fadd(cval[q], ssum[q]);
+          *cellp[q] = nv;
+          if (peer.up || peer.dn) {  // strips only: mirror edge-row cells into the neighbour's mailbox
+            const long long off = cellp[q] - field;
+            const long long ch = off / p.chan_stride;
+            const int col = (int)((off - ch * p.chan_stride) % p.pitch);
+            if (erow[q] == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;
+            if (erow[q] == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
+          }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kOwnThreads, 4)
 k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict__ body_chunks,
                 const uint32_t* __restrict__ keys, const float* __restrict__ vals, uint32_t sentinel,
                 const uint32_t* __restrict__ split, const uint32_t* __restrict__ pmax,
                 const uint32_t* __restrict__ smin, const uint32_t* __restrict__ tail_list,
-                float* __restrict__ field, PeerRows peer) {
-  typedef cub::BlockRadixSort<uint32_t, kOwnThreads, kOwnItems, uint32_t> Sort;
+                float* __restrict__ field, PeerRows peer, const uint32_t* __restrict__ only_if) {
+  if (only_if && *only_if == 0u) return;  // the stencil already applied this tick's deposits (pf_deposit_tile.cuh)
   typedef cub::BlockScan<int, kOwnThreads> Scan;
-  __shared__ union {
-    typename Sort::TempStorage sort;
-    typename Scan::TempStorage scan;
-  } tmp;
-  __shared__ uint32_t lk[kOwnCap];  // local keys of the selected agents, array order / sorted order
+  __shared__ typename Scan::TempStorage scan_tmp;
+  __shared__ OwnScratch u;
+  __shared__ uint32_t lk[kOwnCap];  // local keys of the selected agents (any order)
   __shared__ uint32_t lv[kOwnCap];  // their amounts (bit patterns)
+  __shared__ uint32_t le[kOwnCap];  // their array indices: the summation order inside a cell
   __shared__ uint32_t st_lo[34], st_hi[34];
   __shared__ int st_n;
   __shared__ int tcand[kOwnThreads];  // tail chunks whose bounds meet the current key range
   __shared__ int jrange[2];
+  __shared__ int cnt, ncl;
 
   const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
   const int b = blockIdx.x;
   const int t = threadIdx.x;
+  const int lane = t & 31;
   const int nchunks = min((int)*body_chunks, all_chunks);  // body chunks: binary-searchable bounds
+  const bool vec_ok = ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15u) == 0u;
   if (t == 0) {
     st_lo[0] = split[b];
     st_hi[0] = split[b + 1];
@@ -172,7 +386,7 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
     if (st_n == 0) break;
     const uint32_t lo = st_lo[st_n - 1], hi = st_hi[st_n - 1];
     __syncthreads();
-    if (t == 0) st_n -= 1;
+    if (t == 0) { st_n -= 1; cnt = 0; ncl = 0; }
     // candidate chunks: first j with pmax[j] >= lo ... last j with smin[j] < hi. A 32-ary search by
     // one warp each (two dependent load rounds for 16 K chunks instead of fourteen) run side by side.
     if (t < 64) {
@@ -193,69 +407,84 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
         a = na; z = nz;
       }
       if (l == 0) jrange[w] = z;
+    } else {  // the other warps clear the hash table meanwhile
+      for (int i = t - 64; i < kOwnSlots; i += kOwnThreads - 64) u.h.ht[i] = 0xffffffffu;
+      if (t - 64 < kOwnSlots / 32) u.h.coll[t - 64] = 0u;
     }
     __syncthreads();
     const int j0 = jrange[0], j1 = jrange[1] - 1;
-    __syncthreads();
     const uint32_t span = hi - lo;
-    int count = 0;
     // candidates: body chunks j0..j1 (phase 0), then, 256 at a time, the non-empty tail chunks whose
-    // own bounds meet [lo, hi) (ascending: array order is preserved)
+    // own bounds meet [lo, hi). The agents of [lo, hi) are appended to lk/lv/le in any order (one
+    // shared-memory atomic per warp and chunk, no barrier): their array index travels with them.
     const int nt = (int)body_chunks[1];
     const int nphase = 1 + (nt + kOwnThreads - 1) / kOwnThreads;
     const int nbody = (j1 - j0 + 1 > 0 ? j1 - j0 + 1 : 0);
     for (int phase = 0; phase < nphase; ++phase) {
-    int ncand = nbody;
-    if (phase > 0) {
-      const int it = (phase - 1) * kOwnThreads + t;
-      int has = 0, jt = 0;
-      if (it < nt) {
-        jt = (int)tail_list[it];
-        has = (pmax[jt] >= lo && smin[jt] < hi) ? 1 : 0;
+      int ncand = nbody;
+      if (phase > 0) {
+        const int it = (phase - 1) * kOwnThreads + t;
+        int has = 0, jt = 0;
+        if (it < nt) {
+          jt = (int)tail_list[it];
+          has = (pmax[jt] >= lo && smin[jt] < hi) ? 1 : 0;
+        }
+        int off, total;
+        __syncthreads();
+        Scan(scan_tmp).ExclusiveSum(has, off, total);
+        if (has) tcand[off] = jt;
+        __syncthreads();
+        ncand = total;
       }
-      int off, total;
-      __syncthreads();
-      Scan(tmp.scan).ExclusiveSum(has, off, total);
-      if (has) tcand[off] = jt;
-      __syncthreads();
-      ncand = total;
-    }
-    for (int c = 0; c < ncand; ++c) {
-      const int j = phase == 0 ? j0 + c : tcand[c];
-      const long long e0 = (long long)j * kOwnChunk + 4 * t;
-      uint32_t k4[4], v4[4];
-      int sel[4], nsel = 0;
+      for (int c = 0; c < ncand; ++c) {
+        const int j = phase == 0 ? j0 + c : tcand[c];
+        const long long e0 = (long long)j * kOwnChunk + 4 * t;
+        uint32_t k4[4], v4[4];
+        if (vec_ok && e0 + 3 < n) {
+          const uint4 kk = __ldg(reinterpret_cast<const uint4*>(keys + e0));
+          const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vals + e0));
+          k4[0] = kk.x; k4[1] = kk.y; k4[2] = kk.z; k4[3] = kk.w;
+          v4[0] = vv.x; v4[1] = vv.y; v4[2] = vv.z; v4[3] = vv.w;
+        } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long e = e0 + q;
-        uint32_t key = sentinel;
-        if (e < n) key = keys[e];
-        k4[q] = key;
-        sel[q] = 0;
-        if (key != sentinel) {
-          const uint32_t ch = key / plane;
+          for (int q = 0; q < 4; ++q) {
+            const long long e = e0 + q;
+            k4[q] = e < n ? keys[e] : sentinel;
+            v4[q] = e < n ? __float_as_uint(vals[e]) : 0u;
+          }
+        }
+        bool sel[4];
+        unsigned m4[4];
+        int tot = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t key = k4[q];
+          const uint32_t ch = owner_channel(key, plane);
           const uint32_t sk = key - ch * plane;
-          if (sk >= lo && sk < hi) {
-            sel[q] = 1;
-            k4[q] = ch * span + (sk - lo);
-            v4[q] = __float_as_uint(vals[e]);
-            ++nsel;
+          sel[q] = key != sentinel && sk >= lo && sk < hi;
+          k4[q] = ch * span + (sk - lo);
+          m4[q] = __ballot_sync(0xffffffffu, sel[q]);
+          tot += __popc(m4[q]);
+        }
+        if (tot) {  // warp-uniform
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&cnt, tot);
+          base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int w = base + __popc(m4[q] & ((1u << lane) - 1u));
+            if (sel[q] && w < kOwnCap) {
+              lk[w] = k4[q];
+              lv[w] = v4[q];
+              le[w] = (uint32_t)(e0 + q);
+            }
+            base += __popc(m4[q]);
           }
         }
       }
-      int off, total;
-      Scan(tmp.scan).ExclusiveSum(nsel, off, total);
-      __syncthreads();
-      if (count + total <= kOwnCap) {
-        int w = count + off;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (sel[q]) { lk[w] = k4[q]; lv[w] = v4[q]; ++w; }
-      }
-      count += total;
-    }
     }  // phases
     __syncthreads();
+    const int count = cnt;
 
     if (count == 0) continue;
     if (count > kOwnCap) {
@@ -273,44 +502,44 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
         bool any = false;
         const uint32_t want = (uint32_t)ch * plane + lo;
         for (int phase = 0; phase < nphase; ++phase) {
-        int ncand = nbody;
-        if (phase > 0) {
-          const int it = (phase - 1) * kOwnThreads + t;
-          int has = 0, jt = 0;
-          if (it < nt) {
-            jt = (int)tail_list[it];
-            has = (pmax[jt] >= lo && smin[jt] < hi) ? 1 : 0;
-          }
-          int off, total;
-          __syncthreads();
-          Scan(tmp.scan).ExclusiveSum(has, off, total);
-          if (has) tcand[off] = jt;
-          __syncthreads();
-          ncand = total;
-        }
-        for (int c = 0; c < ncand; ++c) {
-          const int j = phase == 0 ? j0 + c : tcand[c];
-          const long long e0 = (long long)j * kOwnChunk + 4 * t;
-          int nsel = 0;
-          uint32_t v4[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const long long e = e0 + q;
-            if (e < n && keys[e] == want) v4[nsel++] = __float_as_uint(vals[e]);
-          }
-          int off, total;
-          Scan(tmp.scan).ExclusiveSum(nsel, off, total);
-          __syncthreads();
-          for (int q = 0; q < nsel; ++q) lv[off + q] = v4[q];
-          __syncthreads();
-          if (t == 0)
-            for (int q = 0; q < total; ++q) {
-              float a = __uint_as_float(lv[q]);
-              s = any ? fadd(s, a) : a;
-              any = true;
+          int ncand = nbody;
+          if (phase > 0) {
+            const int it = (phase - 1) * kOwnThreads + t;
+            int has = 0, jt = 0;
+            if (it < nt) {
+              jt = (int)tail_list[it];
+              has = (pmax[jt] >= lo && smin[jt] < hi) ? 1 : 0;
             }
-          __syncthreads();
-        }
+            int off, total;
+            __syncthreads();
+            Scan(scan_tmp).ExclusiveSum(has, off, total);
+            if (has) tcand[off] = jt;
+            __syncthreads();
+            ncand = total;
+          }
+          for (int c = 0; c < ncand; ++c) {
+            const int j = phase == 0 ? j0 + c : tcand[c];
+            const long long e0 = (long long)j * kOwnChunk + 4 * t;
+            int nsel = 0;
+            uint32_t v4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const long long e = e0 + q;
+              if (e < n && keys[e] == want) v4[nsel++] = __float_as_uint(vals[e]);
+            }
+            int off, total;
+            Scan(scan_tmp).ExclusiveSum(nsel, off, total);
+            __syncthreads();
+            for (int q = 0; q < nsel; ++q) lv[off + q] = v4[q];
+            __syncthreads();
+            if (t == 0)
+              for (int q = 0; q < total; ++q) {
+                float a = __uint_as_float(lv[q]);
+                s = any ? fadd(s, a) : a;
+                any = true;
+              }
+            __syncthreads();
+          }
         }  // phases
         if (t == 0 && any) {
           const int lr = (int)(lo / (uint32_t)p.W), col = (int)(lo - (uint32_t)lr * (uint32_t)p.W);
@@ -324,67 +553,7 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
       continue;
     }
 
-    // ---- stable block radix sort of the selected agents by cell, then ordered segmented sum
-    uint32_t sk8[kOwnItems], sv8[kOwnItems];
-#pragma unroll
-    for (int q = 0; q < kOwnItems; ++q) {
-      const int e = t * kOwnItems + q;
-      sk8[q] = e < count ? lk[e] : 0xffffffffu;
-      sv8[q] = e < count ? lv[e] : 0u;
-    }
-    __syncthreads();
-    unsigned long long maxkey = (unsigned long long)p.C * span;  // one past the largest local key
-    int end_bit = 1;
-    while ((1ull << end_bit) <= maxkey && end_bit < 32) ++end_bit;  // all-ones padding sorts last
-    Sort(tmp.sort).Sort(sk8, sv8, 0, end_bit);
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < kOwnItems; ++q) {
-      const int e = t * kOwnItems + q;
-      lk[e] = sk8[q];
-      lv[e] = sv8[q];
-    }
-    __syncthreads();
-    // read-modify-write of the touched cells: every thread owns up to kOwnItems segment heads; all
-    // their cell loads are issued first (distinct cells: one writer each), then the adds and stores
-    constexpr int kBatch = 4;
-    for (int q0 = 0; q0 < kOwnItems; q0 += kBatch) {
-      float* cellp[kBatch];
-      float ssum[kBatch], cval[kBatch];
-#pragma unroll
-      for (int q = 0; q < kBatch; ++q) {
-        const int e = t + (q0 + q) * kOwnThreads;
-        cellp[q] = nullptr;
-        if (e < count) {
-          const uint32_t key = lk[e];
-          if (e == 0 || lk[e - 1] != key) {  // segment head
-            float s = __uint_as_float(lv[e]);
-            for (int f = e + 1; f < count && lk[f] == key; ++f) s = fadd(s, __uint_as_float(lv[f]));
-            const uint32_t ch = key / span;
-            const uint32_t sk = lo + (key - ch * span);
-            const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
-            cellp[q] = field + (long long)ch * p.chan_stride + (long long)(lr + 1) * p.pitch + col;
-            ssum[q] = s;
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kBatch; ++q)
-        if (cellp[q]) cval[q] = __ldcg(cellp[q]);
-#pragma unroll
-      for (int q = 0; q < kBatch; ++q)
-        if (cellp[q]) {
-          const float nv = fadd(cval[q], ssum[q]);
-          *cellp[q] = nv;
-          if (peer.up || peer.dn) {  // strips only: mirror edge-row cells into the neighbour's mailbox
-            const uint32_t key = lk[t + (q0 + q) * kOwnThreads];
-            const uint32_t ch = key / span;
-            const uint32_t sk = lo + (key - ch * span);
-            const int lr = (int)(sk / (uint32_t)p.W), col = (int)(sk - (uint32_t)lr * (uint32_t)p.W);
-            if (lr == 0 && peer.up) peer.up[ch * peer.up_cs + col] = nv;
-            if (lr == p.rows - 1 && peer.dn) peer.dn[ch * peer.dn_cs + col] = nv;
-          }
-        }
-    }
+    owner_group_add(p, lo, span, count, lk, lv, le, &u, &ncl, field, peer);
   }
 }
+

@@ -27,6 +27,7 @@ struct PFDev {
   float del_thr;
   // deposit
   float i_explore, i_high, i_homing;
+  int dep_red;  // all intensities >= 1e-30: "cell += sum" may be a reduction at L2 (see pf_deposit_owner.cuh)
   unsigned high_every;
   float move_thr;
   int dep_ch[4], sen_ch[4];

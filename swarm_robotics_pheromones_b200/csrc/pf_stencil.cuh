@@ -28,6 +28,10 @@ struct StencilArgs {
   float dk[PF_MAX_CHANNELS];
   float del_thr;
   PeerRows peer;  // neighbour ghost rows of the NEXT buffer (null when not attached)
+  // next tick's deposits, applied to the output rows (pf_deposit_tile.cuh; TMA variant only)
+  const uint32_t* dep_flag;   // != 0: lists are not usable this tick
+  const uint32_t* dep_count;  // [tile] entries
+  const unsigned char* dep_blk;  // [tile] start[] / col[] / sum[] block
 };
 
 // per-channel constant without dynamic indexing of the kernel parameter block (which would make

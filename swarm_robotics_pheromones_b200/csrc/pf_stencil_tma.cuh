@@ -16,8 +16,14 @@ constexpr int kTmaCols = kTmaWarps * 128;     // columns per CTA
 constexpr int kTmaRowFloats = kTmaCols + 8;   // + 4 halo floats each side
 constexpr int kTmaThreads = kTmaWarps * 32 + 32;  // + producer warp
 
+constexpr int kDepRows = 64;    // rows per CTA when deposits ride along (= kTileRows)
+constexpr int kDepEnt = 1408;   // = kTileEnt
+constexpr int kDepPtrBytes = (kDepRows * kTmaWarps + 8) * 2;  // uint16 list starts (+ end, padded to 16 B)
+constexpr int kDepColBytes = kDepEnt * 2;
+constexpr int kDepBlkBytes = kDepPtrBytes + kDepColBytes + kDepEnt * 4;
+
 struct TmaStencilState {
-  bool attr_set[3][8];
+  bool attr_set[3][9];
   char err[256];
 };
 
@@ -60,13 +66,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // PEER = true only for launches that contain the strip's first / last row while neighbours are attached
 // (the sharded driver launches those two rows on their own), so the streaming instantiation carries
 // no peer logic at all.
-template <int ST, int kStageRows, int kStages, bool PEER>
+// DEP = true: the CTA is one deposit tile (kDepRows x kTmaCols of one channel, whole-field launch);
+// its (cell, sum) lists arrive by three more bulk copies and the producer warp adds them to the rows
+// the consumers have just stored (reductions performed by the L2).
+template <int ST, int kStageRows, int kStages, bool PEER, bool DEP>
 __global__ void __launch_bounds__(kTmaThreads)
 k_stencil_tma(StencilArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * kStageRows * kTmaRowFloats);
   uint64_t* empty = full + kStages;
+  uint64_t* dep_bar = empty + kStages;  // the tile's deposit lists have landed
+  uint64_t* fin = dep_bar + 1;          // every consumer warp has issued its last store
+  // 16 B aligned: ring rows are 4128 B, 2 * kStages + 2 barriers of 8 B
+  unsigned char* dblk =
+      smem_raw + (((size_t)kStages * kStageRows * kTmaRowFloats * 4 + (2 * kStages + 2) * 8 + 15) & ~(size_t)15);
+  const uint16_t* dstart = reinterpret_cast<const uint16_t*>(dblk);
+  const uint16_t* dcol = reinterpret_cast<const uint16_t*>(dblk + kDepPtrBytes);
+  const float* dsum = reinterpret_cast<const float*>(dblk + kDepPtrBytes + kDepColBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.z;
@@ -83,10 +100,20 @@ k_stencil_tma(StencilArgs a) {
   const uint32_t row_bytes = (uint32_t)(g1 - g0) * 4u;
   const int dst_off = g0 - (c0 - 4);
 
+  uint32_t ndep = 0u;
+  long long tile = 0;
+  if (DEP) {
+    tile = ((long long)ch * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (*a.dep_flag == 0u) ndep = a.dep_count[tile];  // uniform per CTA
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kTmaWarps);
+    }
+    if (DEP) {
+      mbar_init(dep_bar, 1);
+      mbar_init(fin, kTmaWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -95,9 +122,26 @@ k_stencil_tma(StencilArgs a) {
   const float* __restrict__ base = a.cur + ch * a.chan_stride + a.pitch;
 
   if (warp == kTmaWarps) {
-    // ===== producer: one elected lane =====
-    if (lane == 0) {
-      for (int it = 0; it < niter; ++it) {
+    // ===== producer: one elected lane issues the copies =====
+    // DEP: the whole warp also applies the tile's deposits, kStages + 1 stages behind the copies it
+    // issues: once the consumers have released stage it - kStages (the wait below), every one of
+    // them has issued its stores for the output rows of stage it - kStages - 1 (program order before
+    // its arrive; arrive = release, wait = acquire), so a reduction sent to those cells now lands
+    // on the stored value, in L2, microseconds after the store: nxt[cell] = stencil value + sum.
+    float* const otile = a.nxt + ch * a.chan_stride + a.pitch + (long long)r0 * a.pitch + c0;
+    const int nrows = r1 - r0;
+    auto dep_rows = [&](int lr_b, int lr_e) {  // output rows [lr_b, lr_e) of the tile
+      lr_b = max(lr_b, 0);
+      lr_e = min(lr_e, nrows);
+      if (lr_b >= lr_e) return;
+      const int e1 = dstart[lr_e * kTmaWarps];
+      for (int e = dstart[lr_b * kTmaWarps] + lane; e < e1; e += 32) {
+        const uint32_t dc = dcol[e];  // row << 10 | column, both within the tile
+        atomicAdd(otile + (long long)(dc >> 10) * a.pitch + (dc & 1023u), dsum[e]);
+      }
+    };
+    for (int it = 0; it < niter; ++it) {
+      if (lane == 0) {
         const int s = it % kStages;
         const uint32_t ph = (uint32_t)(it / kStages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
@@ -110,7 +154,27 @@ k_stencil_tma(StencilArgs a) {
           bulk_g2s(ring + ((size_t)s * kStageRows + k) * kTmaRowFloats + dst_off,
                    base + (long long)r * a.pitch + g0, row_bytes, &full[s]);
         }
+        if (DEP && it == 0 && ndep) {  // the tile's deposit lists, behind the first stage
+          const uint32_t col_bytes = (ndep * 2u + 15u) & ~15u, sum_bytes = (ndep * 4u + 15u) & ~15u;
+          const unsigned char* src = a.dep_blk + tile * kDepBlkBytes;
+          mbar_expect_tx(dep_bar, (uint32_t)kDepPtrBytes + col_bytes + sum_bytes);
+          bulk_g2s(dblk, src, kDepPtrBytes, dep_bar);
+          bulk_g2s(dblk + kDepPtrBytes, src + kDepPtrBytes, col_bytes, dep_bar);
+          bulk_g2s(dblk + kDepPtrBytes + kDepColBytes, src + kDepPtrBytes + kDepColBytes, sum_bytes, dep_bar);
+        }
       }
+      if (DEP && ndep && it > kStages) {  // uniform per CTA
+        __syncwarp();
+        mbar_wait(dep_bar, 0u);  // completes once; later waits on the finished phase return at once
+        const int j = it - kStages - 1;
+        dep_rows(j * kStageRows - 2, (j + 1) * kStageRows - 2);
+      }
+    }
+    if (DEP && ndep) {  // the last kStages + 1 stages, after the consumers' last stores
+      __syncwarp();
+      mbar_wait(fin, 0u);
+      mbar_wait(dep_bar, 0u);
+      dep_rows(max(niter - kStages - 1, 0) * kStageRows - 2, nrows);
     }
     return;
   }
@@ -173,21 +237,32 @@ k_stencil_tma(StencilArgs a) {
       }
     }
   }
+  if (DEP && ndep) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(fin);
+  }
 }
 
-template <int ST, int R, int S, bool PEER>
+template <int ST, int R, int S, bool PEER, bool DEP = false>
 static int tma_launch_one(TmaStencilState* st, int slot, const StencilArgs& a, dim3 grid, cudaStream_t s) {
-  const size_t smem = (size_t)S * R * kTmaRowFloats * sizeof(float) + 2 * S * sizeof(uint64_t);
+  size_t smem = (size_t)S * R * kTmaRowFloats * sizeof(float) + (2 * S + 2) * sizeof(uint64_t);
+  if (DEP) smem = ((smem + 15) & ~(size_t)15) + kDepBlkBytes;
   const int sti = ST == 0 ? 0 : (ST == 5 ? 1 : 2);
   if (!st->attr_set[sti][slot]) {
-    cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<ST, R, S, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<ST, R, S, PEER, DEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       snprintf(st->err, sizeof(st->err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PF_ECUDA;
     }
     st->attr_set[sti][slot] = true;
+    if (getenv("PF_DEBUG_OCC")) {
+      int occ = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stencil_tma<ST, R, S, PEER, DEP>, kTmaThreads, smem);
+      fprintf(stderr, "[pherofield] k_stencil_tma<%d,%d,%d,%d,%d>: %zu B smem, %d CTAs/SM\n", ST, R, S, (int)PEER,
+              (int)DEP, smem, occ);
+    }
   }
-  k_stencil_tma<ST, R, S, PEER><<<grid, kTmaThreads, smem, s>>>(a);
+  k_stencil_tma<ST, R, S, PEER, DEP><<<grid, kTmaThreads, smem, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(st->err, sizeof(st->err), "launch: %s", cudaGetErrorString(e));
@@ -229,4 +304,16 @@ static int tma_stencil_launch(TmaStencilState* st, int shape, const pf_config& c
   if (shape == 3) PF_TMA_DISPATCH(4, 6, 3);   //  99 KB: 2 CTAs/SM, deeper
   PF_TMA_DISPATCH(4, 4, 0);                   //  66 KB: 3 CTAs/SM
 #undef PF_TMA_DISPATCH
+}
+
+// Whole-field launch with the next tick's deposits riding along: CTA = deposit tile (kDepRows rows x
+// kTmaCols columns x one channel), ring shape 4 x 4. The caller has checked W % 4 == 0, W >= 128,
+// stencil != 0, no peers.
+static int tma_stencil_launch_dep(TmaStencilState* st, const PFDev& d, StencilArgs a, cudaStream_t s) {
+  a.r_begin = 0;
+  a.r_end = d.rows;
+  a.rows_per_cta = kDepRows;
+  dim3 grid((d.W + kTmaCols - 1) / kTmaCols, (d.rows + kDepRows - 1) / kDepRows, d.C);
+  if (d.stencil == 5) return tma_launch_one<5, 4, 4, false, true>(st, 8, a, grid, s);
+  return tma_launch_one<9, 4, 4, false, true>(st, 8, a, grid, s);
 }

@@ -16,6 +16,7 @@
 
 #include "../../include/pherofield.h"
 #include "pf_agents.cuh"
+#include "pf_deposit_tile.cuh"
 #include "pf_device.cuh"
 #include "pf_stencil.cuh"
 #include "pf_stencil_tma.cuh"
@@ -26,7 +27,7 @@ struct GraphKey {
   const void *x, *y, *theta, *wl, *wr, *meta, *scratch;
   long long n, cap;
   uint32_t mask;
-  int parity, variant, rpc;
+  int parity, variant, rpc, tile;
 };
 
 struct pf_handle {
@@ -60,6 +61,14 @@ struct pf_handle {
   int n_sm, wave_keys, wave_agents;
   // owner-computes deposit (pf_deposit_owner.cuh): valid after pf_agents_sort for these arrays
   uint32_t *own_split, *own_cmin, *own_cmax, *own_pmax, *own_smin, *own_body, *own_tail;
+  // deposit fused into the stencil (pf_deposit_tile.cuh): per-tile bins, per-tile lists, status flag
+  uint32_t *tile_bcnt, *tile_bkey, *tile_bidx, *tile_flag, *tile_count;
+  float* tile_bval;
+  unsigned char* tile_blk;
+  long long tile_alloc;   // tiles allocated
+  int no_tile_deposit;
+  bool tile_pending;      // the last stencil launch was asked to apply the next tick's deposits
+  unsigned long long tile_attempts, g_tile_attempts;
   long long own_alloc;      // chunks allocated
   long long own_n;          // agent slots the splitters were built for (0 = invalid)
   const float* own_x;
@@ -113,6 +122,13 @@ static int set_err(pf_handle* h, int code, const char* fmt, ...) {
 
 static bool is_sharded(const pf_handle* h) { return h->cfg.row0 > 0 || h->cfg.row1 < h->cfg.H; }
 static void graph_drop(pf_handle* h);
+
+static void tile_free(pf_handle* h) {
+  void** arrs[7] = {(void**)&h->tile_bcnt, (void**)&h->tile_bkey, (void**)&h->tile_bidx, (void**)&h->tile_flag,
+                    (void**)&h->tile_count, (void**)&h->tile_bval, (void**)&h->tile_blk};
+  for (auto pp : arrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+  h->tile_alloc = 0;
+}
 
 static inline unsigned blocks_for(long long n, int threads) {
   return (unsigned)((n + threads - 1) / threads);
@@ -228,6 +244,7 @@ static void derive(pf_handle* h) {
   }
   d.del_thr = c.delete_threshold;
   d.i_explore = c.intensity_explore; d.i_high = c.intensity_high; d.i_homing = c.intensity_homing;
+  d.dep_red = (c.intensity_explore >= 1e-30f && c.intensity_high >= 1e-30f && c.intensity_homing >= 1e-30f) ? 1 : 0;
   d.high_every = (unsigned)c.high_every;
   d.move_thr = c.move_threshold;
   for (int s = 0; s < 4; ++s) { d.dep_ch[s] = c.deposit_channel[s]; d.sen_ch[s] = c.sense_channel[s]; }
@@ -336,6 +353,7 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->own_smin) cudaFree(h->own_smin);
   if (h->own_body) cudaFree(h->own_body);
   if (h->own_tail) cudaFree(h->own_tail);
+  tile_free(h);
   if (h->counters) cudaFree(h->counters);
   if (h->d_sum) cudaFree(h->d_sum);
   if (h->peer_flags) cudaFree(h->peer_flags);
@@ -499,7 +517,7 @@ static PeerRows peer_rows(const pf_handle* h, int k) {
   return r;
 }
 
-static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) {
+static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, bool with_deposits = false) {
   if (r_begin >= r_end) return PF_OK;
   const PFDev& d = h->dev;
   StencilArgs a;
@@ -512,6 +530,14 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s) 
   for (int k = 0; k < PF_MAX_CHANNELS; ++k) { a.keep[k] = d.keep[k]; a.dk[k] = d.dk[k]; }
   a.del_thr = d.del_thr;
   a.peer = peer_rows(h, h->cur ^ 1);
+  a.dep_flag = nullptr; a.dep_count = nullptr; a.dep_blk = nullptr;
+  if (with_deposits) {  // tile_ok() holds: whole field, TMA ring, CTA = deposit tile
+    a.dep_flag = h->tile_flag; a.dep_count = h->tile_count; a.dep_blk = h->tile_blk;
+    int rc = tma_stencil_launch_dep(&h->tma, d, a, s);
+    if (rc != PF_OK) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
+    h->launches++;
+    return PF_OK;
+  }
   const int nrows = r_end - r_begin;
   if (d.W % 4 != 0) {
     dim3 grid(blocks_for(d.W, 256), nrows, d.C);
@@ -589,6 +615,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (!h) return PF_EINVAL;
   if (option == PF_OPT_OVERLAP_AGENTS) { h->overlap_agents = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_FUSED_KEYS) { h->no_fused_keys = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_NO_TILE_DEPOSIT) { h->no_tile_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_OWNER_DEPOSIT) { h->no_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_FORCE_OWNER_DEPOSIT) { h->force_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
@@ -605,6 +632,71 @@ extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_ct
 // ---------------------------------------------------------------------------------------------
 // K2 launch
 // ---------------------------------------------------------------------------------------------
+static bool owner_ready(const pf_handle* h, const pf_agents* a);
+
+extern "C" int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_back) {
+  if (!h) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  uint32_t fb = 0;
+  if (h->tile_flag) {
+    PF_CUDA(h, cudaDeviceSynchronize());
+    PF_CUDA(h, cudaMemcpy(&fb, h->tile_flag + 1, sizeof(fb), cudaMemcpyDeviceToHost));
+  }
+  if (attempted) *attempted = h->tile_attempts;
+  if (fell_back) *fell_back = fb;
+  return PF_OK;
+}
+
+// Can this tick's stencil apply the next tick's deposits (pf_deposit_tile.cuh)? Needs the sort-free
+// deposit (its kernels are the device-side fallback), the TMA stencil in its default shape on the
+// whole field, and no second stream.
+static bool tile_ok(const pf_handle* h, const pf_agents* a) {
+  const PFDev& d = h->dev;
+  return !h->no_tile_deposit && !is_sharded(h) && !h->overlap_agents && owner_ready(h, a) && d.stencil != 0 &&
+         d.dep_red &&
+         d.W % 4 == 0 && d.W >= 512 && (h->variant == 0 || h->variant == 2) && h->rows_per_cta <= 0 &&
+         kTileRows == kDepRows && kTileEnt == kDepEnt && kTileCols == kTmaCols && kTileWarps == kTmaWarps &&
+         kTileBlkBytes == kDepBlkBytes;
+}
+
+static TileGeom tile_geom(const pf_handle* h) {
+  TileGeom g;
+  g.nx = (h->dev.W + kTileCols - 1) / kTileCols;
+  g.ny = (h->dev.rows + kTileRows - 1) / kTileRows;
+  g.W = h->dev.W;
+  g.plane = (uint32_t)((long long)h->dev.rows * h->dev.W);
+  return g;
+}
+
+// keys_in / vals_in (array order, from the move kernel) -> per-tile lists for the stencil
+static int tile_prepare(pf_handle* h, long long n, cudaStream_t s) {
+  const TileGeom g = tile_geom(h);
+  const long long ntiles = (long long)g.nx * g.ny * h->dev.C;
+  if (h->tile_alloc < ntiles) {
+    tile_free(h);
+    PF_CUDA(h, cudaMalloc(&h->tile_bcnt, sizeof(uint32_t) * ntiles));
+    PF_CUDA(h, cudaMemset(h->tile_bcnt, 0, sizeof(uint32_t) * ntiles));
+    PF_CUDA(h, cudaMalloc(&h->tile_count, sizeof(uint32_t) * ntiles));
+    PF_CUDA(h, cudaMalloc(&h->tile_flag, 2 * sizeof(uint32_t)));  // [0] status of this tick, [1] fallbacks so far
+    PF_CUDA(h, cudaMemset(h->tile_flag, 0, 2 * sizeof(uint32_t)));
+    PF_CUDA(h, cudaMalloc(&h->tile_bkey, sizeof(uint32_t) * ntiles * kOwnCap));
+    PF_CUDA(h, cudaMalloc(&h->tile_bval, sizeof(float) * ntiles * kOwnCap));
+    PF_CUDA(h, cudaMalloc(&h->tile_bidx, sizeof(uint32_t) * ntiles * kOwnCap));
+    PF_CUDA(h, cudaMalloc(&h->tile_blk, (size_t)ntiles * kTileBlkBytes));
+    h->tile_alloc = ntiles;
+  }
+  const uint32_t* keys_in = (const uint32_t*)h->scratch;
+  const float* vals_in = (const float*)(keys_in + 2 * h->cap);
+  PF_CUDA(h, cudaMemsetAsync(h->tile_flag, 0, sizeof(uint32_t), s));
+  k_tile_bin<<<wave_grid(n, h->wave_keys), 256, 0, s>>>(n, g, keys_in, vals_in, h->sentinel, h->tile_bcnt,
+                                                        h->tile_bkey, h->tile_bval, h->tile_bidx, h->tile_flag);
+  PF_LAUNCH_CHECK(h);
+  k_tile_group<<<(unsigned)ntiles, kOwnThreads, 0, s>>>(h->tile_bcnt, h->tile_bkey, h->tile_bval, h->tile_bidx,
+                                                        h->tile_flag, h->tile_count, h->tile_blk);
+  PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
 // is the owner-computes deposit usable for these agent arrays? (splitters from the last pf_agents_sort)
 static bool owner_ready(const pf_handle* h, const pf_agents* a) {
   return !h->no_owner_deposit && (h->own_worth || h->force_owner_deposit) && h->own_n == a->n &&
@@ -612,17 +704,18 @@ static bool owner_ready(const pf_handle* h, const pf_agents* a) {
 }
 
 // keys_in / vals_in (array order) -> field, without a global sort
-static int owner_sum(pf_handle* h, long long n, cudaStream_t s) {
+// only_if (device flag, may be null): do the work only if *only_if != 0
+static int owner_sum(pf_handle* h, long long n, cudaStream_t s, uint32_t* only_if = nullptr) {
   h->mig_flags_n = 0;
   const uint32_t* keys_in = (const uint32_t*)h->scratch;
   const float* vals_in = (const float*)(keys_in + 2 * h->cap);
   const int nchunks = (int)((n + kOwnChunk - 1) / kOwnChunk);
   k_owner_bounds<<<1, 1024, 0, s>>>(nchunks, h->own_body, h->own_cmin, h->own_cmax, h->own_pmax, h->own_smin,
-                                    h->own_tail);
+                                    h->own_tail, only_if);
   PF_LAUNCH_CHECK(h);
   k_deposit_owner<<<nchunks, kOwnThreads, 0, s>>>(h->dev, n, nchunks, h->own_body, keys_in, vals_in, h->sentinel,
                                                   h->own_split, h->own_pmax, h->own_smin, h->own_tail,
-                                                  h->buf[h->cur], peer_rows(h, h->cur));
+                                                  h->buf[h->cur], peer_rows(h, h->cur), only_if);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -830,11 +923,14 @@ static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream
     PF_CUDA(h, cudaEventRecord(pe[0], s));
   }
   if (now >= h->start_delay && (mask & PF_STEP_DEPOSIT) && a->n > 0) {  // deposit_pheromone, sup:577
-    if (keys_ready)  // keys came from the previous tick's move kernel
+    if (keys_ready && h->tile_pending)  // the last stencil was asked to apply them: only_if it could not
+      rc = owner_sum(h, a->n, s, h->tile_flag);
+    else if (keys_ready)  // keys came from the previous tick's move kernel
       rc = owner_ready(h, a) ? owner_sum(h, a->n, s) : sort_and_sum(h, a->n, s);
     else rc = pf_agents_deposit(h, a, (void*)s);
     if (rc) return rc;
   }
+  h->tile_pending = false;
   *keys_ready_out = false;
   if (pe) PF_CUDA(h, cudaEventRecord(pe[1], s));
   const bool run_agents = a->n > 0 && (mask & (PF_STEP_SENSE | PF_STEP_MOVE));
@@ -856,12 +952,18 @@ static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream
     rc = launch_agents_step(h, a, flags, nullptr, as, emit);
     if (rc) return rc;
     *keys_ready_out = emit;
+    if (emit && (mask & PF_STEP_FIELD) && tile_ok(h, a)) {  // hand the next tick's deposits to the stencil
+      rc = tile_prepare(h, a->n, as);
+      if (rc) return rc;
+      h->tile_pending = true;
+      h->tile_attempts++;
+    }
     if (pe) PF_CUDA(h, cudaEventRecord(pe[4], as));
     if (fork) PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
   }
   if (pe) PF_CUDA(h, cudaEventRecord(pe[5], s));
   if (mask & PF_STEP_FIELD) {
-    rc = launch_stencil(h, 0, h->dev.rows, s);
+    rc = launch_stencil(h, 0, h->dev.rows, s, h->tile_pending);
     if (rc) return rc;
   }
   if (pe) {
@@ -889,10 +991,12 @@ static int graph_prepare(pf_handle* h, const pf_agents* a, uint32_t mask, cudaSt
   memset(&k, 0, sizeof(k));
   k.x = a->x; k.y = a->y; k.theta = a->theta; k.wl = a->wl; k.wr = a->wr; k.meta = a->meta;
   k.n = a->n; k.mask = mask; k.parity = h->cur; k.variant = h->variant; k.rpc = h->rows_per_cta;
+  k.tile = (h->tile_pending ? 1 : 0) | (tile_ok(h, a) ? 2 : 0) | (owner_ready(h, a) ? 4 : 0);
   k.scratch = h->scratch; k.cap = h->cap;
   if (h->g_exec && memcmp(&k, &h->g_key, sizeof(k)) == 0) return PF_OK;
   graph_drop(h);
   const uint64_t ticks0 = h->ticks, launches0 = h->launches;
+  const unsigned long long attempts0 = h->tile_attempts;
   // capture on the handle's own stream (the caller's may be the legacy default stream, which cannot
   // be captured); the instantiated graph is then launched into the caller's stream
   (void)s;
@@ -904,6 +1008,8 @@ static int graph_prepare(pf_handle* h, const pf_agents* a, uint32_t mask, cudaSt
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(cs, &g);
   h->g_nodes = h->launches - launches0;
+  h->g_tile_attempts = h->tile_attempts - attempts0;
+  h->tile_attempts = attempts0;
   h->ticks = ticks0;       // capturing enqueues nothing: undo the host-side bookkeeping
   h->launches = launches0;  // (two buffer flips cancel)
   if (rc != PF_OK || e != cudaSuccess || !g || !kr) {
@@ -927,6 +1033,7 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   bool keys_ready = false;
+  h->tile_pending = false;
   int t = 0;
   // CUDA-graph path for launch-bound (small) problems: tick 0 normally (builds keys), then pairs of
   // steady-state ticks replayed from one graph, the last tick normally (must not pre-bump the
@@ -946,6 +1053,7 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
           PF_CUDA(h, cudaGraphLaunch(h->g_exec, s));
           h->ticks += 2;
           h->launches += h->g_nodes;
+          h->tile_attempts += h->g_tile_attempts;
         }
         t += 2 * pairs;
       } else {

@@ -294,6 +294,12 @@ class PheroField:
         self._ck(self._L.pf_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def tile_stats(self):
+        """(ticks whose stencil carried the next tick's deposits, how many of them fell back)"""
+        a, f = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.pf_tile_stats(self._h, C.byref(a), C.byref(f)))
+        return a.value, f.value
+
     def profile(self, on: bool):
         self._ck(self._L.pf_profile_enable(self._h, 1 if on else 0))
 

@@ -543,3 +543,79 @@ def test_owner_computes_deposit_standalone_calls_and_fractional_amount_order():
     assert (sw.to_numpy()["meta"] == a_np.meta).all()
     assert_bitexact(g.snapshot(), o.field, "fractional amounts, owner-computes vs sequential oracle")
     g.close()
+
+
+# ----------------------------------------------------------------------------- deposit fused into the stencil
+@pytest.mark.parametrize("stencil", [5, 9])
+def test_deposit_riding_on_the_stencil_bitexact(stencil):
+    # pf_step hands tick t+1's deposits to tick t's stencil (pf_deposit_tile.cuh): 3 x 2 tiles per
+    # channel with ragged last tiles (160 = 64 + 64 + 32 rows, 1536 = 1024 + 512 columns), two
+    # channels, a few hundred shared cells per tile, fractional amounts (summation order matters)
+    cfg = make_cfg(160, 1536, 2, stencil)
+    cfg.fsm = 1
+    cfg.intensity_explore, cfg.intensity_high, cfg.intensity_homing = 0.3, 1.7, 0.9
+    cfg.nest_x, cfg.nest_y = 0.8, 7.0
+    cfg.food_x[0], cfg.food_y[0] = 1.1, 9.0
+    cfg.food_radius = 0.3
+    rng = np.random.default_rng(77)
+    n = 4100   # the two full 64 x 1024 tiles of a channel get about 550 depositors each (limit 768 cells)
+    x, y, th, _ = rand_agents(rng, cfg, n, margin=0.02)
+    x[:100] = (0.40 + rng.uniform(0, 0.06, 100)).astype(np.float32)   # 100 agents on a 6 x 6 cell patch
+    y[:100] = (3.00 + rng.uniform(0, 0.06, 100)).astype(np.float32)
+    st = rng.integers(1, 3, n)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    g.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
+    g2 = PheroField(cfg)
+    g2.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
+    g2.set_option(abi.OPT_NO_TILE_DEPOSIT, 1)
+    sw, sw2 = Swarm(x, y, th, st), Swarm(x, y, th, st)
+    g.sort_agents(sw)
+    g2.sort_agents(sw2)
+    ticks = 0
+    for k in (1, 2, 5, 40):
+        o.tick(a_np, k)
+        g.step(sw, k)
+        g2.step(sw2, k)
+        ticks += k
+        assert_bitexact(g.snapshot(), o.field, f"fused field after {ticks} ticks")
+        assert_bitexact(g2.snapshot(), o.field, f"unfused field after {ticks} ticks")
+    got = sw.to_numpy()
+    order = np.argsort(got["gid"], kind="stable")
+    for f in ("x", "y", "theta", "wl", "wr"):
+        assert_bitexact(got[f][order], getattr(a_np, f), f)
+    assert (got["meta"][order] == a_np.meta).all()
+    attempted, fell_back = g.tile_stats()
+    assert attempted == (2 - 1) + (5 - 1) + (40 - 1) and fell_back == 0   # every tick but the last of a call
+    assert g2.tile_stats() == (0, 0)
+    g.close(); g2.close()
+
+
+def test_deposit_riding_on_the_stencil_falls_back_when_a_tile_is_crowded():
+    # 5000 agents inside one tile (bin overflow) and 1500 of them on a 4 x 4 patch (shared-cell list
+    # overflow): the flag is raised on the device, the stencil leaves its output alone and the next
+    # tick's own deposit kernels do the work — same bits either way
+    cfg = make_cfg(128, 2048, 1, 9)
+    rng = np.random.default_rng(78)
+    n = 9000
+    x, y, th, _ = rand_agents(rng, cfg, n, margin=0.02)
+    x[:5000] = (0.10 + rng.uniform(0, 0.40, 5000)).astype(np.float32)
+    y[:5000] = (12.0 + rng.uniform(0, 4.00, 5000)).astype(np.float32)
+    x[:1500] = (0.30 + rng.uniform(0, 0.04, 1500)).astype(np.float32)
+    y[:1500] = (14.0 + rng.uniform(0, 0.04, 1500)).astype(np.float32)
+    st = rng.integers(1, 3, n)
+    a_np = dense.AgentsNP(x, y, th, st)
+    o = dense.DenseOracle(cfg)
+    g = PheroField(cfg)
+    g.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
+    sw = Swarm(x, y, th, st)
+    g.sort_agents(sw)
+    for k in (3, 20):
+        o.tick(a_np, k)
+        g.step(sw, k)
+        assert_bitexact(g.snapshot(), o.field, "field with crowded tiles")
+    attempted, fell_back = g.tile_stats()
+    assert attempted == 2 + 19 and fell_back == attempted
+    assert g.counters().deposits == int(o.counters[8])
+    g.close()
