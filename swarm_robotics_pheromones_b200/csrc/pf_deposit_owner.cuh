@@ -169,9 +169,9 @@ union OwnScratch {
 // slot of the shared-memory hash table; a collision bit says whether any other agent shares the
 // cell. All agents of shared cells go on the short list u->h.clist (*ncl entries; more than
 // kOwnShared means "crowded": the list is then incomplete). Returns this thread's mask of items
-// (e = t + q * kOwnThreads) that sit in shared cells. The caller has cleared ht / coll / *ncl and
+// (e = t + q * kOwnThreads) that sit in shared cells. The caller has cleared h->ht / h->coll / *ncl and
 // synchronised; ends with a barrier.
-__device__ __forceinline__ unsigned owner_hash_build(int count, const uint32_t* lk, OwnScratch* u, int* ncl) {
+__device__ __forceinline__ unsigned owner_hash_build(int count, const uint32_t* lk, OwnHash* h, int* ncl) {
   const int t = threadIdx.x;
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
@@ -180,10 +180,10 @@ __device__ __forceinline__ unsigned owner_hash_build(int count, const uint32_t* 
       const uint32_t key = lk[e];
       uint32_t slot = (key * 2654435761u) >> (32 - kOwnSlotBits);
       while (true) {
-        const uint32_t old = atomicCAS(&u->h.ht[slot], 0xffffffffu, (uint32_t)e);
+        const uint32_t old = atomicCAS(&h->ht[slot], 0xffffffffu, (uint32_t)e);
         if (old == 0xffffffffu) break;
         if (lk[old] == key) {  // the slot belongs to this cell already
-          atomicOr(&u->h.coll[slot >> 5], 1u << (slot & 31u));
+          atomicOr(&h->coll[slot >> 5], 1u << (slot & 31u));
           break;
         }
         slot = (slot + 1u) & (kOwnSlots - 1);
@@ -198,11 +198,11 @@ __device__ __forceinline__ unsigned owner_hash_build(int count, const uint32_t* 
     if (e < count) {
       const uint32_t key = lk[e];
       uint32_t slot = (key * 2654435761u) >> (32 - kOwnSlotBits);
-      while (lk[u->h.ht[slot]] != key) slot = (slot + 1u) & (kOwnSlots - 1);  // find the cell's slot again
-      if ((u->h.coll[slot >> 5] >> (slot & 31u)) & 1u) {
+      while (lk[h->ht[slot]] != key) slot = (slot + 1u) & (kOwnSlots - 1);  // find the cell's slot again
+      if ((h->coll[slot >> 5] >> (slot & 31u)) & 1u) {
         shared8 |= 1u << q;
         const int pos = atomicAdd(ncl, 1);
-        if (pos < kOwnShared) u->h.clist[pos] = (uint16_t)e;
+        if (pos < kOwnShared) h->clist[pos] = (uint16_t)e;
       }
     }
   }
@@ -214,10 +214,10 @@ __device__ __forceinline__ unsigned owner_hash_build(int count, const uint32_t* 
 // its own amount) becomes the cell's amounts summed in array order — the summation order of the
 // global-sort path and of the oracle. nshared <= kOwnShared.
 __device__ __forceinline__ bool owner_shared_sum(int e, int nshared, const uint32_t* lk, const uint32_t* lv,
-                                                 const uint32_t* le, const OwnScratch* u, float* s) {
+                                                 const uint32_t* le, const OwnHash* h, float* s) {
   const uint32_t key = lk[e], mine = le[e];
   for (int i = 0; i < nshared; ++i) {
-    const int c = (int)u->h.clist[i];
+    const int c = (int)h->clist[i];
     if (lk[c] == key && le[c] < mine) return false;
   }
   uint32_t last = mine;  // next larger array index with this cell, until there is none
@@ -225,7 +225,7 @@ __device__ __forceinline__ bool owner_shared_sum(int e, int nshared, const uint3
     uint32_t best = 0xffffffffu;
     int bi = -1;
     for (int i = 0; i < nshared; ++i) {
-      const int c = (int)u->h.clist[i];
+      const int c = (int)h->clist[i];
       const uint32_t ec = le[c];
       if (lk[c] == key && ec > last && ec < best) { best = ec; bi = c; }
     }
@@ -246,7 +246,7 @@ __device__ __forceinline__ void owner_group_add(const PFDev& p, uint32_t lo, uin
                                                 const PeerRows& peer) {
   const int t = threadIdx.x;
   const bool use_red = p.dep_red && !peer.up && !peer.dn;  // mirrored edge rows need the new value
-  const unsigned shared8 = owner_hash_build(count, lk, u, ncl);
+  const unsigned shared8 = owner_hash_build(count, lk, &u->h, ncl);
     const int nshared = *ncl;
 
     if (nshared > kOwnShared) {
@@ -309,7 +309,7 @@ __device__ __forceinline__ void owner_group_add(const PFDev& p, uint32_t lo, uin
           const uint32_t key = lk[e];
           float s = __uint_as_float(lv[e]);
           bool head = true;
-          if ((shared8 >> (q0 + q)) & 1u) head = owner_shared_sum(e, nshared, lk, lv, le, u, &s);
+          if ((shared8 >> (q0 + q)) & 1u) head = owner_shared_sum(e, nshared, lk, lv, le, &u->h, &s);
           if (head) {
             const uint32_t ch = key / span;
             const uint32_t sk = lo + (key - ch * span);

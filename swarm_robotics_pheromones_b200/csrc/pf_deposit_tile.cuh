@@ -9,9 +9,8 @@
 //   k_tile_bin    one streaming pass: every depositing agent goes into the bin of the stencil tile
 //                 (channel, 64 rows, 1024 columns — one stencil CTA) that will write its cell;
 //   k_tile_group  one CTA per tile: group the bin by cell (shared-memory hash, array-order sums —
-//                 the same rounding as every other deposit path), then lay the (column, sum) pairs
-//                 out by (row, consumer warp) of the stencil CTA;
-//   k_stencil_tma<.., DEP> pulls its tile's lists into shared memory with three bulk copies; its
+//                 the same rounding as every other deposit path) into a list of (cell, sum) pairs;
+//   k_stencil_tma<.., DEP> pulls its tile's list into shared memory with two bulk copies; its
 //                 producer warp sends each sum as a reduction (performed by the L2) to the cell
 //                 a few microseconds after the consumer warps stored it, while the line is still
 //                 in L2: nxt[cell] = fadd(stencil value, sum) — bit for bit what a separate
@@ -26,17 +25,21 @@
 
 constexpr int kTileRows = 64;    // stencil rows per CTA on this path
 constexpr int kTileCols = 1024;  // = kTmaCols
-constexpr int kTileWarps = 8;    // = kTmaWarps: column slices of 128
-constexpr int kTileLists = kTileRows * kTileWarps;
 constexpr int kTileEnt = 1408;   // distinct deposited cells a tile can hand to the stencil
-// one tile's block in global memory, copied piecewise into the stencil CTA's shared memory:
-//   uint16 start[kTileLists + 1 (+7 pad)]   list i = entries [start[i], start[i+1])
-//   uint16 col[kTileEnt]                    row << 10 | column, within the tile
+// The stencil streams its rows in stages of 4 (ring shape 4 x 4); stage j produces the output rows
+// [4j - 2, 4j + 2) of the tile. Entries are grouped by stage so that the stencil finds the ones for
+// the rows it has just stored without searching.
+constexpr int kTileStageRows = 4;
+constexpr int kTileGroups = (kTileRows + 2 + kTileStageRows - 1) / kTileStageRows;  // 17
+// one tile's block in global memory, copied into the stencil CTA's shared memory (as much as is used):
+//   uint16 start[24]        group g = entries [start[g], start[g+1]), g < kTileGroups
+//   uint16 cell[kTileEnt]   row << 10 | column, within the tile
 //   float  sum[kTileEnt]
-constexpr int kTilePtrBytes = (kTileLists + 8) * 2;
+constexpr int kTilePtrBytes = 48;
 constexpr int kTileColBytes = kTileEnt * 2;
 constexpr int kTileBlkBytes = kTilePtrBytes + kTileColBytes + kTileEnt * 4;
-static_assert(kTilePtrBytes % 16 == 0 && kTileColBytes % 16 == 0 && kTileBlkBytes % 16 == 0, "bulk copy alignment");
+static_assert(kTileGroups + 1 <= kTilePtrBytes / 2 && kTileGroups <= 32, "group starts");
+static_assert(kTileColBytes % 16 == 0 && kTileBlkBytes % 16 == 0, "bulk copy alignment");
 
 struct TileGeom {
   int nx, ny;      // tiles per row of tiles / per channel plane column
@@ -87,92 +90,121 @@ k_tile_bin(long long n, TileGeom g, const uint32_t* __restrict__ keys, const flo
   }
 }
 
-// per tile: tcount = number of (cell, sum) entries; block = start[] / col[] / sum[] as laid out above,
-// list = row * 8 + (column >> 7)
+// per tile: tcount = number of (cell, sum) entries, block = start[] / cell[] / sum[] as laid out above
 __global__ void __launch_bounds__(kOwnThreads, 4)
 k_tile_group(uint32_t* __restrict__ bcnt, const uint32_t* __restrict__ bkey, const float* __restrict__ bval,
              const uint32_t* __restrict__ bidx, uint32_t* __restrict__ flag, uint32_t* __restrict__ tcount,
              unsigned char* __restrict__ tblk) {
-  typedef cub::BlockScan<uint32_t, kOwnThreads> Scan;
-  __shared__ OwnScratch u;
-  __shared__ typename Scan::TempStorage scan_tmp;
+  __shared__ OwnHash hs;
   __shared__ uint32_t lk[kOwnCap], lv[kOwnCap], le[kOwnCap];
-  __shared__ uint32_t lcnt[kTileLists], lpos[kTileLists];
   __shared__ int ncl;
+  __shared__ uint32_t nent, gcnt[32], gpos[32];
   const int tile = blockIdx.x, t = threadIdx.x;
+  const long long base = (long long)tile * kOwnCap;
+  // the first half of the bin is fetched together with its fill count (one round trip less)
+  constexpr int kEarly = kOwnItems / 2;
+  uint32_t k_[kEarly], v_[kEarly], e_[kEarly];
   const uint32_t raw = bcnt[tile];
-  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kEarly; ++q) {
+    const long long e = base + t + q * kOwnThreads;
+    k_[q] = __ldcs(bkey + e);
+    v_[q] = __float_as_uint(__ldcs(bval + e));
+    e_[q] = __ldcs(bidx + e);
+  }
+  for (int i = t; i < kOwnSlots; i += kOwnThreads) hs.ht[i] = 0xffffffffu;
+  if (t < kOwnSlots / 32) hs.coll[t] = 0u;
+  if (t < 32) gcnt[t] = 0u;
+  __syncthreads();  // every thread has read the count
   if (t == 0) {
     bcnt[tile] = 0u;
     ncl = 0;
+    nent = 0u;
     if (raw == 0u) tcount[tile] = 0u;
   }
   if (raw == 0u || raw > (uint32_t)kOwnCap) return;  // empty, or overflowed in k_tile_bin (flag is set)
   const int count = (int)raw;
-  const long long base = (long long)tile * kOwnCap;
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
     const int e = t + q * kOwnThreads;
     if (e < count) {
-      lk[e] = __ldcs(bkey + base + e);
-      lv[e] = __float_as_uint(__ldcs(bval + base + e));
-      le[e] = __ldcs(bidx + base + e);
+      if (q < kEarly) {
+        lk[e] = k_[q]; lv[e] = v_[q]; le[e] = e_[q];
+      } else {
+        lk[e] = __ldcs(bkey + base + e);
+        lv[e] = __float_as_uint(__ldcs(bval + base + e));
+        le[e] = __ldcs(bidx + base + e);
+      }
     }
   }
-  for (int i = t; i < kOwnSlots; i += kOwnThreads) u.h.ht[i] = 0xffffffffu;
-  if (t < kOwnSlots / 32) u.h.coll[t] = 0u;
-  for (int i = t; i < kTileLists; i += kOwnThreads) { lcnt[i] = 0u; lpos[i] = 0u; }
   __syncthreads();
-  const unsigned shared8 = owner_hash_build(count, lk, &u, &ncl);
+  const unsigned shared8 = owner_hash_build(count, lk, &hs, &ncl);
   const int nshared = ncl;
   if (nshared > kOwnShared) {  // crowded tile: leave this tick to the regular deposit kernels
     if (t == 0) *flag = 1u;
     return;
   }
-  // heads: the cell's ordered sum replaces the head's own amount; count them per list
+  // pass 1: every cell's head gets the cell's ordered sum and is counted in its stage group
+  const int lane = t & 31;
   unsigned head8 = 0u;
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
     const int e = t + q * kOwnThreads;
+    int g = -1;
     if (e < count) {
       float s = __uint_as_float(lv[e]);
       bool head = true;
-      if ((shared8 >> q) & 1u) head = owner_shared_sum(e, nshared, lk, lv, le, &u, &s);
+      if ((shared8 >> q) & 1u) {
+        head = owner_shared_sum(e, nshared, lk, lv, le, &hs, &s);
+        if (head) lv[e] = __float_as_uint(s);  // read by nobody else: members skip heads
+      }
       if (head) {
         head8 |= 1u << q;
-        if ((shared8 >> q) & 1u) lv[e] = __float_as_uint(s);  // read by nobody else: members skip heads
-        const uint32_t key = lk[e];
-        atomicAdd(&lcnt[(key >> 10) * kTileWarps + ((key & 1023u) >> 7)], 1u);
+        g = (int)((lk[e] >> 10) + 2u) / kTileStageRows;
       }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, g);
+    if (g >= 0 && lane == __ffs(peers) - 1) atomicAdd(&gcnt[g], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  unsigned char* blk = tblk + (long long)tile * kTileBlkBytes;
+  if (t < 32) {  // exclusive scan of the group sizes
+    const uint32_t c = t < kTileGroups ? gcnt[t] : 0u;
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (t >= d) inc += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    gpos[t] = inc - c;
+    if (total <= (uint32_t)kTileEnt) {
+      if (t <= kTileGroups) reinterpret_cast<uint16_t*>(blk)[t] = (uint16_t)(inc - c);  // start[kTileGroups] = total
+    }
+    if (t == 0) {
+      nent = total;
+      if (total > (uint32_t)kTileEnt) *flag = 1u;
+      else tcount[tile] = total;
     }
   }
   __syncthreads();
-  // exclusive scan of the list sizes (2 lists per thread)
-  uint32_t c2[2] = {lcnt[2 * t], lcnt[2 * t + 1]}, o2[2], total;
-  Scan(scan_tmp).ExclusiveSum(c2, o2, total);
-  if (total > (uint32_t)kTileEnt) {  // block-uniform
-    if (t == 0) *flag = 1u;
-    return;
-  }
-  lpos[2 * t] = o2[0];
-  lpos[2 * t + 1] = o2[1];
-  unsigned char* blk = tblk + (long long)tile * kTileBlkBytes;
-  uint16_t* start = reinterpret_cast<uint16_t*>(blk);
-  uint16_t* ecol = reinterpret_cast<uint16_t*>(blk + kTilePtrBytes);
+  if (nent > (uint32_t)kTileEnt) return;
+  // pass 2: place the heads
+  uint16_t* ecell = reinterpret_cast<uint16_t*>(blk + kTilePtrBytes);
   float* esum = reinterpret_cast<float*>(blk + kTilePtrBytes + kTileColBytes);
-  reinterpret_cast<uint32_t*>(start)[t] = o2[0] | (o2[1] << 16);
-  if (t == 0) {
-    start[kTileLists] = (uint16_t)total;
-    tcount[tile] = total;
-  }
-  __syncthreads();
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
     const int e = t + q * kOwnThreads;
-    if ((head8 >> q) & 1u) {
-      const uint32_t key = lk[e];
-      const uint32_t w = atomicAdd(&lpos[(key >> 10) * kTileWarps + ((key & 1023u) >> 7)], 1u);
-      ecol[w] = (uint16_t)key;  // row << 10 | column
+    const bool head = (head8 >> q) & 1u;
+    const uint32_t key = head ? lk[e] : 0u;
+    const int g = head ? (int)((key >> 10) + 2u) / kTileStageRows : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, g);
+    if (head) {
+      const int leader = __ffs(peers) - 1;
+      uint32_t w = 0u;
+      if (lane == leader) w = atomicAdd(&gpos[g], (uint32_t)__popc(peers));
+      w = __shfl_sync(peers, w, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      ecell[w] = (uint16_t)key;  // row << 10 | column
       esum[w] = __uint_as_float(lv[e]);
     }
   }

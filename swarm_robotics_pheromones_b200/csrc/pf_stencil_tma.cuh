@@ -18,8 +18,8 @@ constexpr int kTmaThreads = kTmaWarps * 32 + 32;  // + producer warp
 
 constexpr int kDepRows = 64;    // rows per CTA when deposits ride along (= kTileRows)
 constexpr int kDepEnt = 1408;   // = kTileEnt
-constexpr int kDepPtrBytes = (kDepRows * kTmaWarps + 8) * 2;  // uint16 list starts (+ end, padded to 16 B)
-constexpr int kDepColBytes = kDepEnt * 2;
+constexpr int kDepPtrBytes = 48;           // uint16 start[] of the per-stage entry groups (= kTilePtrBytes)
+constexpr int kDepColBytes = kDepEnt * 2;  // uint16 row << 10 | column
 constexpr int kDepBlkBytes = kDepPtrBytes + kDepColBytes + kDepEnt * 4;
 
 struct TmaStencilState {
@@ -67,7 +67,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // (the sharded driver launches those two rows on their own), so the streaming instantiation carries
 // no peer logic at all.
 // DEP = true: the CTA is one deposit tile (kDepRows x kTmaCols of one channel, whole-field launch);
-// its (cell, sum) lists arrive by three more bulk copies and the producer warp adds them to the rows
+// its (cell, sum) list arrives by two more bulk copies and the producer warp adds them to the rows
 // the consumers have just stored (reductions performed by the L2).
 template <int ST, int kStageRows, int kStages, bool PEER, bool DEP>
 __global__ void __launch_bounds__(kTmaThreads)
@@ -76,11 +76,13 @@ k_stencil_tma(StencilArgs a) {
   float* ring = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * kStageRows * kTmaRowFloats);
   uint64_t* empty = full + kStages;
+  static_assert(!DEP || kStageRows == 4, "deposit entries are grouped by stages of 4 rows (pf_deposit_tile.cuh)");
   uint64_t* dep_bar = empty + kStages;  // the tile's deposit lists have landed
   uint64_t* fin = dep_bar + 1;          // every consumer warp has issued its last store
-  // 16 B aligned: ring rows are 4128 B, 2 * kStages + 2 barriers of 8 B
+  uint32_t* progress = reinterpret_cast<uint32_t*>(fin + 1);  // last iteration whose `empty` wait the producer passed
+  // 16 B aligned: ring rows are 4128 B, 2 * kStages + 3 slots of 8 B
   unsigned char* dblk =
-      smem_raw + (((size_t)kStages * kStageRows * kTmaRowFloats * 4 + (2 * kStages + 2) * 8 + 15) & ~(size_t)15);
+      smem_raw + (((size_t)kStages * kStageRows * kTmaRowFloats * 4 + (2 * kStages + 3) * 8 + 15) & ~(size_t)15);
   const uint16_t* dstart = reinterpret_cast<const uint16_t*>(dblk);
   const uint16_t* dcol = reinterpret_cast<const uint16_t*>(dblk + kDepPtrBytes);
   const float* dsum = reinterpret_cast<const float*>(dblk + kDepPtrBytes + kDepColBytes);
@@ -114,6 +116,7 @@ k_stencil_tma(StencilArgs a) {
     if (DEP) {
       mbar_init(dep_bar, 1);
       mbar_init(fin, kTmaWarps);
+      *progress = 0u;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -123,28 +126,19 @@ k_stencil_tma(StencilArgs a) {
 
   if (warp == kTmaWarps) {
     // ===== producer: one elected lane issues the copies =====
-    // DEP: the whole warp also applies the tile's deposits, kStages + 1 stages behind the copies it
-    // issues: once the consumers have released stage it - kStages (the wait below), every one of
+    // DEP: the other 31 lanes apply the tile's deposits, kStages + 1 stages behind the copies being
+    // issued: once the consumers have released stage it - kStages (the producer's wait), every one of
     // them has issued its stores for the output rows of stage it - kStages - 1 (program order before
     // its arrive; arrive = release, wait = acquire), so a reduction sent to those cells now lands
     // on the stored value, in L2, microseconds after the store: nxt[cell] = stencil value + sum.
     float* const otile = a.nxt + ch * a.chan_stride + a.pitch + (long long)r0 * a.pitch + c0;
-    const int nrows = r1 - r0;
-    auto dep_rows = [&](int lr_b, int lr_e) {  // output rows [lr_b, lr_e) of the tile
-      lr_b = max(lr_b, 0);
-      lr_e = min(lr_e, nrows);
-      if (lr_b >= lr_e) return;
-      const int e1 = dstart[lr_e * kTmaWarps];
-      for (int e = dstart[lr_b * kTmaWarps] + lane; e < e1; e += 32) {
-        const uint32_t dc = dcol[e];  // row << 10 | column, both within the tile
-        atomicAdd(otile + (long long)(dc >> 10) * a.pitch + (dc & 1023u), dsum[e]);
-      }
-    };
-    for (int it = 0; it < niter; ++it) {
-      if (lane == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < niter; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (uint32_t)(it / kStages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
+        if (DEP && ndep)  // a counter, not the barrier's parity: the deposit lanes may lag by any amount
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(progress)), "r"((uint32_t)it) : "memory");
         const int first = it * kStageRows;
         const int cnt = min(kStageRows, nstream - first);
         mbar_expect_tx(&full[s], row_bytes * (uint32_t)cnt);
@@ -154,27 +148,35 @@ k_stencil_tma(StencilArgs a) {
           bulk_g2s(ring + ((size_t)s * kStageRows + k) * kTmaRowFloats + dst_off,
                    base + (long long)r * a.pitch + g0, row_bytes, &full[s]);
         }
-        if (DEP && it == 0 && ndep) {  // the tile's deposit lists, behind the first stage
+        if (DEP && it == 0 && ndep) {  // the tile's deposit list, behind the first stage
           const uint32_t col_bytes = (ndep * 2u + 15u) & ~15u, sum_bytes = (ndep * 4u + 15u) & ~15u;
           const unsigned char* src = a.dep_blk + tile * kDepBlkBytes;
           mbar_expect_tx(dep_bar, (uint32_t)kDepPtrBytes + col_bytes + sum_bytes);
-          bulk_g2s(dblk, src, kDepPtrBytes, dep_bar);
-          bulk_g2s(dblk + kDepPtrBytes, src + kDepPtrBytes, col_bytes, dep_bar);
+          bulk_g2s(dblk, src, (uint32_t)kDepPtrBytes + col_bytes, dep_bar);  // start[] and cell[] are adjacent
           bulk_g2s(dblk + kDepPtrBytes + kDepColBytes, src + kDepPtrBytes + kDepColBytes, sum_bytes, dep_bar);
         }
       }
-      if (DEP && ndep && it > kStages) {  // uniform per CTA
-        __syncwarp();
-        mbar_wait(dep_bar, 0u);  // completes once; later waits on the finished phase return at once
-        const int j = it - kStages - 1;
-        dep_rows(j * kStageRows - 2, (j + 1) * kStageRows - 2);
-      }
-    }
-    if (DEP && ndep) {  // the last kStages + 1 stages, after the consumers' last stores
-      __syncwarp();
-      mbar_wait(fin, 0u);
+    } else if (DEP && ndep) {
+      // lanes 1..31 (diverged from the producer lane for good; they only meet it at mbarriers)
+      auto dep_stages = [&](int jb, int je) {  // the entries of stages [jb, je): output rows [4 jb - 2, 4 je - 2)
+        const int e1 = dstart[je];
+        for (int e = dstart[jb] + lane - 1; e < e1; e += 31) {
+          const uint32_t dc = dcol[e];  // row << 10 | column, both within the tile
+          atomicAdd(otile + (long long)(dc >> 10) * a.pitch + (dc & 1023u), dsum[e]);
+        }
+      };
       mbar_wait(dep_bar, 0u);
-      dep_rows(max(niter - kStages - 1, 0) * kStageRows - 2, nrows);
+      for (int it = kStages + 1; it < niter; ++it) {
+        while (true) {  // stage it - kStages released by every consumer warp?
+          uint32_t seen;
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(progress)) : "memory");
+          if ((int)seen >= it) break;
+          __nanosleep(200);
+        }
+        dep_stages(it - kStages - 1, it - kStages);
+      }
+      mbar_wait(fin, 0u);  // the last kStages + 1 stages, after the consumers' last stores
+      dep_stages(max(niter - kStages - 1, 0), niter);
     }
     return;
   }
@@ -245,7 +247,7 @@ k_stencil_tma(StencilArgs a) {
 
 template <int ST, int R, int S, bool PEER, bool DEP = false>
 static int tma_launch_one(TmaStencilState* st, int slot, const StencilArgs& a, dim3 grid, cudaStream_t s) {
-  size_t smem = (size_t)S * R * kTmaRowFloats * sizeof(float) + (2 * S + 2) * sizeof(uint64_t);
+  size_t smem = (size_t)S * R * kTmaRowFloats * sizeof(float) + (2 * S + 3) * sizeof(uint64_t);
   if (DEP) smem = ((smem + 15) & ~(size_t)15) + kDepBlkBytes;
   const int sti = ST == 0 ? 0 : (ST == 5 ? 1 : 2);
   if (!st->attr_set[sti][slot]) {

@@ -655,8 +655,8 @@ static bool tile_ok(const pf_handle* h, const pf_agents* a) {
   return !h->no_tile_deposit && !is_sharded(h) && !h->overlap_agents && owner_ready(h, a) && d.stencil != 0 &&
          d.dep_red &&
          d.W % 4 == 0 && d.W >= 512 && (h->variant == 0 || h->variant == 2) && h->rows_per_cta <= 0 &&
-         kTileRows == kDepRows && kTileEnt == kDepEnt && kTileCols == kTmaCols && kTileWarps == kTmaWarps &&
-         kTileBlkBytes == kDepBlkBytes;
+         kTileRows == kDepRows && kTileEnt == kDepEnt && kTileCols == kTmaCols && kTileBlkBytes == kDepBlkBytes &&
+         kTilePtrBytes == kDepPtrBytes;
 }
 
 static TileGeom tile_geom(const pf_handle* h) {
