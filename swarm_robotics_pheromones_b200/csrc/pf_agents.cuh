@@ -1,7 +1,7 @@
 // pf_agents.cuh — K2 (deterministic deposit) and K3 (sense -> decide -> move) kernels.
 #pragma once
 #include "pf_device.cuh"
-#include "pf_deposit_owner.cuh"
+#include "pf_deposit_tile.cuh"
 
 // ------------------------------------------------------------------------------------------
 // K2a: sort keys. key = local linear cell index ((ch*rows + lr)*W + col); agents that do not
@@ -225,7 +225,7 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
               uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters,
               unsigned long long* __restrict__ mig_flags, uint32_t* __restrict__ next_keys,
               float* __restrict__ next_vals, uint32_t sentinel, uint32_t* __restrict__ cmin,
-              uint32_t* __restrict__ cmax) {
+              uint32_t* __restrict__ cmax, TileBins tb) {
   __shared__ unsigned int hist[9];  // 0..5 decisions, 6 grabbed, 7 delivered, 8 deposits (next tick)
   if (threadIdx.x < 9) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -373,8 +373,9 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
       if (next_keys) {
         // the next tick's deposit rule, evaluated here on the state it would read (identical to
         // k_deposit_keys_agents; pf_step only asks for it when that deposit is certain to run)
-        uint32_t key = sentinel;
+        uint32_t key = sentinel, local = 0u;
         float amt = 0.0f;
+        int tile = -1;
         if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && moved) {
           uint32_t cnt = (nm >> PF_META_COUNT_SHIFT) + 1u;
           amt = (st == PF_STATE_SEARCHING) ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
@@ -382,12 +383,15 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
           nm = (nm & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
           int r, q;
           bool inside = pf_cell(p, x, y, r, q);
-          if (inside && r >= p.row0 && r < p.row1)
+          if (inside && r >= p.row0 && r < p.row1) {
             key = (uint32_t)(((long long)p.dep_ch[st] * p.rows + (r - p.row0)) * p.W + q);
+            if (tb.bcnt) tile = tile_of(tb, p.dep_ch[st], r - p.row0, q, &local);
+          }
           atomicAdd(&hist[8], 1u);
         }
         next_keys[i] = key;
         next_vals[i] = amt;
+        if (tb.bcnt) tile_bin_put(tb, __activemask(), tile, local, amt, (uint32_t)i);  // pf_deposit_tile.cuh
         if (cmin) {
           const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
           owner_note_bounds(cmin, cmax, i / kOwnChunk, key % plane, key != sentinel);

@@ -369,11 +369,14 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
   __shared__ int cnt, ncl;
 
   const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
-  const int b = blockIdx.x;
   const int t = threadIdx.x;
   const int lane = t & 31;
   const int nchunks = min((int)*body_chunks, all_chunks);  // body chunks: binary-searchable bounds
   const bool vec_ok = ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15u) == 0u;
+  // one key range per CTA (grid = all_chunks), or a small grid striding over the ranges (the
+  // stand-by launch behind the fused deposit, which nearly always returns at the first line)
+  for (int b = blockIdx.x; b < all_chunks; b += gridDim.x) {
+  __syncthreads();
   if (t == 0) {
     st_lo[0] = split[b];
     st_hi[0] = split[b + 1];
@@ -555,5 +558,6 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
 
     owner_group_add(p, lo, span, count, lk, lv, le, &u, &ncl, field, peer);
   }
+  }  // key ranges of this CTA
 }
 

@@ -6,8 +6,9 @@
 // every cell of the new buffer anyway, and the amounts of deposit(t+1) are known before stencil(t)
 // starts (the move kernel of tick t has just produced them). So:
 //
-//   k_tile_bin    one streaming pass: every depositing agent goes into the bin of the stencil tile
-//                 (channel, 64 rows, 1024 columns — one stencil CTA) that will write its cell;
+//   move kernel   (k_agents_step, which produces the next tick's deposits anyway) puts every
+//                 depositing agent into the bin of the stencil tile (channel, 64 rows, 1024
+//                 columns — one stencil CTA) that will write its cell;
 //   k_tile_group  one CTA per tile: group the bin by cell (shared-memory hash, array-order sums —
 //                 the same rounding as every other deposit path) into a list of (cell, sum) pairs;
 //   k_stencil_tma<.., DEP> pulls its tile's list into shared memory with two bulk copies; its
@@ -41,57 +42,48 @@ constexpr int kTileBlkBytes = kTilePtrBytes + kTileColBytes + kTileEnt * 4;
 static_assert(kTileGroups + 1 <= kTilePtrBytes / 2 && kTileGroups <= 32, "group starts");
 static_assert(kTileColBytes % 16 == 0 && kTileBlkBytes % 16 == 0, "bulk copy alignment");
 
-struct TileGeom {
-  int nx, ny;      // tiles per row of tiles / per channel plane column
-  int W;           // columns
-  uint32_t plane;  // cells per channel
+// bins of the stencil tiles: kOwnCap records (cell within the tile, amount, array index) each
+struct TileBins {
+  uint32_t* bcnt;  // null: no binning
+  uint32_t* bkey;
+  float* bval;
+  uint32_t* bidx;
+  uint32_t* flag;
+  int nx, ny;      // tiles along a row / along a column of one channel plane
 };
 
-__global__ void __launch_bounds__(256)
-k_tile_bin(long long n, TileGeom g, const uint32_t* __restrict__ keys, const float* __restrict__ vals,
-           uint32_t sentinel, uint32_t* __restrict__ bcnt, uint32_t* __restrict__ bkey,
-           float* __restrict__ bval, uint32_t* __restrict__ bidx, uint32_t* __restrict__ flag) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
+// Called by every thread of `act` (converged); tile < 0 = nothing to put. One counter update per
+// (warp, tile): agents that are neighbours in the array are mostly neighbours on the grid.
+__device__ __forceinline__ void tile_bin_put(const TileBins& tb, unsigned act, int tile, uint32_t local, float v,
+                                             uint32_t index) {
   const int lane = threadIdx.x & 31;
-  for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
-    const long long i = i0 + threadIdx.x;
-    uint32_t key = sentinel;
-    float v = 0.0f;
-    if (i < n) {
-      key = __ldcs(keys + i);
-      v = __ldcs(vals + i);
-    }
-    int tile = -1;
-    uint32_t local = 0u;
-    if (key != sentinel) {
-      const uint32_t ch = owner_channel(key, g.plane);
-      const uint32_t sk = key - ch * g.plane;
-      const uint32_t lr = sk / (uint32_t)g.W, col = sk - lr * (uint32_t)g.W;
-      const uint32_t ty = lr / kTileRows, tx = col / kTileCols;
-      tile = (int)((ch * (uint32_t)g.ny + ty) * (uint32_t)g.nx + tx);
-      local = (lr - ty * kTileRows) * kTileCols + (col - tx * kTileCols);
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, tile);  // one counter update per (warp, tile)
-    if (tile >= 0) {
-      const int leader = __ffs(peers) - 1;
-      uint32_t base = 0u;
-      if (lane == leader) base = atomicAdd(bcnt + tile, (uint32_t)__popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      if (pos < (uint32_t)kOwnCap) {
-        const long long w = (long long)tile * kOwnCap + pos;
-        bkey[w] = local;
-        bval[w] = v;
-        bidx[w] = (uint32_t)i;
-      } else {
-        *flag = 1u;
-      }
+  const unsigned peers = __match_any_sync(act, tile);
+  if (tile >= 0) {
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0u;
+    if (lane == leader) base = atomicAdd(tb.bcnt + tile, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    if (pos < (uint32_t)kOwnCap) {
+      const long long w = (long long)tile * kOwnCap + pos;
+      tb.bkey[w] = local;
+      tb.bval[w] = v;
+      tb.bidx[w] = index;
+    } else {
+      *tb.flag = 1u;
     }
   }
 }
 
+// tile and cell-within-tile of (channel, strip-local row, column)
+__device__ __forceinline__ int tile_of(const TileBins& tb, int ch, int lr, int col, uint32_t* local) {
+  const int ty = lr / kTileRows, tx = col / kTileCols;
+  *local = (uint32_t)((lr - ty * kTileRows) * kTileCols + (col - tx * kTileCols));
+  return (ch * tb.ny + ty) * tb.nx + tx;
+}
+
 // per tile: tcount = number of (cell, sum) entries, block = start[] / cell[] / sum[] as laid out above
-__global__ void __launch_bounds__(kOwnThreads, 4)
+__global__ void __launch_bounds__(kOwnThreads, 5)
 k_tile_group(uint32_t* __restrict__ bcnt, const uint32_t* __restrict__ bkey, const float* __restrict__ bval,
              const uint32_t* __restrict__ bidx, uint32_t* __restrict__ flag, uint32_t* __restrict__ tcount,
              unsigned char* __restrict__ tblk) {
@@ -122,7 +114,7 @@ k_tile_group(uint32_t* __restrict__ bcnt, const uint32_t* __restrict__ bkey, con
     nent = 0u;
     if (raw == 0u) tcount[tile] = 0u;
   }
-  if (raw == 0u || raw > (uint32_t)kOwnCap) return;  // empty, or overflowed in k_tile_bin (flag is set)
+  if (raw == 0u || raw > (uint32_t)kOwnCap) return;  // empty, or overflowed while binning (flag is set)
   const int count = (int)raw;
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {

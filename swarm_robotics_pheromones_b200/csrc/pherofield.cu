@@ -16,7 +16,6 @@
 
 #include "../../include/pherofield.h"
 #include "pf_agents.cuh"
-#include "pf_deposit_tile.cuh"
 #include "pf_device.cuh"
 #include "pf_stencil.cuh"
 #include "pf_stencil_tma.cuh"
@@ -659,19 +658,10 @@ static bool tile_ok(const pf_handle* h, const pf_agents* a) {
          kTilePtrBytes == kDepPtrBytes;
 }
 
-static TileGeom tile_geom(const pf_handle* h) {
-  TileGeom g;
-  g.nx = (h->dev.W + kTileCols - 1) / kTileCols;
-  g.ny = (h->dev.rows + kTileRows - 1) / kTileRows;
-  g.W = h->dev.W;
-  g.plane = (uint32_t)((long long)h->dev.rows * h->dev.W);
-  return g;
-}
-
-// keys_in / vals_in (array order, from the move kernel) -> per-tile lists for the stencil
-static int tile_prepare(pf_handle* h, long long n, cudaStream_t s) {
-  const TileGeom g = tile_geom(h);
-  const long long ntiles = (long long)g.nx * g.ny * h->dev.C;
+// before the move kernel: storage, cleared status flag, the bins the kernel fills
+static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb) {
+  const int nx = (h->dev.W + kTileCols - 1) / kTileCols, ny = (h->dev.rows + kTileRows - 1) / kTileRows;
+  const long long ntiles = (long long)nx * ny * h->dev.C;
   if (h->tile_alloc < ntiles) {
     tile_free(h);
     PF_CUDA(h, cudaMalloc(&h->tile_bcnt, sizeof(uint32_t) * ntiles));
@@ -685,12 +675,16 @@ static int tile_prepare(pf_handle* h, long long n, cudaStream_t s) {
     PF_CUDA(h, cudaMalloc(&h->tile_blk, (size_t)ntiles * kTileBlkBytes));
     h->tile_alloc = ntiles;
   }
-  const uint32_t* keys_in = (const uint32_t*)h->scratch;
-  const float* vals_in = (const float*)(keys_in + 2 * h->cap);
   PF_CUDA(h, cudaMemsetAsync(h->tile_flag, 0, sizeof(uint32_t), s));
-  k_tile_bin<<<wave_grid(n, h->wave_keys), 256, 0, s>>>(n, g, keys_in, vals_in, h->sentinel, h->tile_bcnt,
-                                                        h->tile_bkey, h->tile_bval, h->tile_bidx, h->tile_flag);
-  PF_LAUNCH_CHECK(h);
+  tb->bcnt = h->tile_bcnt; tb->bkey = h->tile_bkey; tb->bval = h->tile_bval; tb->bidx = h->tile_bidx;
+  tb->flag = h->tile_flag; tb->nx = nx; tb->ny = ny;
+  return PF_OK;
+}
+
+// after the move kernel: bins -> per-tile lists for the stencil
+static int tile_finish(pf_handle* h, cudaStream_t s) {
+  const int nx = (h->dev.W + kTileCols - 1) / kTileCols, ny = (h->dev.rows + kTileRows - 1) / kTileRows;
+  const long long ntiles = (long long)nx * ny * h->dev.C;
   k_tile_group<<<(unsigned)ntiles, kOwnThreads, 0, s>>>(h->tile_bcnt, h->tile_bkey, h->tile_bval, h->tile_bidx,
                                                         h->tile_flag, h->tile_count, h->tile_blk);
   PF_LAUNCH_CHECK(h);
@@ -713,9 +707,11 @@ static int owner_sum(pf_handle* h, long long n, cudaStream_t s, uint32_t* only_i
   k_owner_bounds<<<1, 1024, 0, s>>>(nchunks, h->own_body, h->own_cmin, h->own_cmax, h->own_pmax, h->own_smin,
                                     h->own_tail, only_if);
   PF_LAUNCH_CHECK(h);
-  k_deposit_owner<<<nchunks, kOwnThreads, 0, s>>>(h->dev, n, nchunks, h->own_body, keys_in, vals_in, h->sentinel,
-                                                  h->own_split, h->own_pmax, h->own_smin, h->own_tail,
-                                                  h->buf[h->cur], peer_rows(h, h->cur), only_if);
+  // stand-by behind the fused deposit: one wave of CTAs striding over the key ranges
+  const int grid = only_if ? (nchunks < 4 * h->n_sm ? nchunks : 4 * h->n_sm) : nchunks;
+  k_deposit_owner<<<grid, kOwnThreads, 0, s>>>(h->dev, n, nchunks, h->own_body, keys_in, vals_in, h->sentinel,
+                                               h->own_split, h->own_pmax, h->own_smin, h->own_tail,
+                                               h->buf[h->cur], peer_rows(h, h->cur), only_if);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -795,7 +791,7 @@ extern "C" int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y,
 }
 
 static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s,
-                              bool emit_next_keys = false) {
+                              bool emit_next_keys = false, const TileBins* bins = nullptr) {
   // on a strip, the move kernel also emits the leave-up / leave-down flags pf_migrate_pack needs
   unsigned long long* mig = nullptr;
   if (is_sharded(h) && (flags & PF_STEP_MOVE) && h->scratch && a->n <= h->cap) {
@@ -805,6 +801,8 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
   }
   uint32_t* nk = nullptr;
   float* nv = nullptr;
+  TileBins no_bins;
+  memset(&no_bins, 0, sizeof(no_bins));
   if (emit_next_keys && !mig) {  // keys_in / vals_in of the sort scratch, for the next tick's deposit
     nk = (uint32_t*)h->scratch;
     nv = (float*)(nk + 2 * h->cap);
@@ -813,7 +811,8 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
                                                      a->theta, a->wl, a->wr, a->meta, dec, h->counters, mig,
                                                      nk, nv, h->sentinel,
                                                      (nk && owner_ready(h, a)) ? h->own_cmin : nullptr,
-                                                     (nk && owner_ready(h, a)) ? h->own_cmax : nullptr);
+                                                     (nk && owner_ready(h, a)) ? h->own_cmax : nullptr,
+                                                     (nk && bins) ? *bins : no_bins);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -949,11 +948,18 @@ static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream
     const double next = h->t0 + (double)(h->ticks + 1) * (double)h->cfg.dt;
     const bool emit = emit_next && !h->no_fused_keys && (mask & PF_STEP_DEPOSIT) && next >= h->start_delay &&
                       !is_sharded(h);
-    rc = launch_agents_step(h, a, flags, nullptr, as, emit);
+    // hand the next tick's deposits to this tick's stencil? (pf_deposit_tile.cuh)
+    const bool tile_try = emit && (mask & PF_STEP_FIELD) && tile_ok(h, a);
+    TileBins bins;
+    if (tile_try) {
+      rc = tile_begin(h, as, &bins);
+      if (rc) return rc;
+    }
+    rc = launch_agents_step(h, a, flags, nullptr, as, emit, tile_try ? &bins : nullptr);
     if (rc) return rc;
     *keys_ready_out = emit;
-    if (emit && (mask & PF_STEP_FIELD) && tile_ok(h, a)) {  // hand the next tick's deposits to the stencil
-      rc = tile_prepare(h, a->n, as);
+    if (tile_try) {
+      rc = tile_finish(h, as);
       if (rc) return rc;
       h->tile_pending = true;
       h->tile_attempts++;
