@@ -156,7 +156,7 @@ __device__ __forceinline__ uint32_t owner_channel(uint32_t key, uint32_t plane) 
 
 typedef cub::BlockRadixSort<unsigned long long, kOwnThreads, kOwnItems, uint32_t> OwnSort;
 struct OwnHash {
-  uint32_t ht[kOwnSlots];         // cell -> index into lk[] of the agent that claimed the slot
+  uint32_t ht[kOwnSlots];         // cell keys (0xffffffff = free slot)
   uint32_t coll[kOwnSlots / 32];  // slot holds more than one agent
   uint16_t clist[kOwnShared];     // indices of all agents of shared cells
 };
@@ -165,45 +165,52 @@ union OwnScratch {
   typename OwnSort::TempStorage sort;  // crowded ranges only
 };
 
-// Hash phase shared by the deposit kernels. lk[0..count) = cell keys (any order). Each key claims one
-// slot of the shared-memory hash table; a collision bit says whether any other agent shares the
-// cell. All agents of shared cells go on the short list u->h.clist (*ncl entries; more than
-// kOwnShared means "crowded": the list is then incomplete). Returns this thread's mask of items
-// (e = t + q * kOwnThreads) that sit in shared cells. The caller has cleared h->ht / h->coll / *ncl and
-// synchronised; ends with a barrier.
+// Shared-memory hash set of the cell keys of one CTA's agents (open addressing, linear probing; a
+// key is never 0xffffffff). A slot holds the key that claimed it; its collision bit says that more
+// than one agent has that key, i.e. the cell is shared.
+__device__ __forceinline__ uint32_t owner_hash_slot(uint32_t key) { return (key * 2654435761u) >> (32 - kOwnSlotBits); }
+
+__device__ __forceinline__ void owner_hash_insert(uint32_t key, OwnHash* h) {
+  uint32_t slot = owner_hash_slot(key);
+  while (true) {
+    const uint32_t old = atomicCAS(&h->ht[slot], 0xffffffffu, key);
+    if (old == 0xffffffffu) break;
+    if (old == key) {  // the slot belongs to this cell already
+      atomicOr(&h->coll[slot >> 5], 1u << (slot & 31u));
+      break;
+    }
+    slot = (slot + 1u) & (kOwnSlots - 1);
+  }
+}
+
+// after all inserts (and a barrier)
+__device__ __forceinline__ bool owner_hash_shared(uint32_t key, const OwnHash* h) {
+  uint32_t slot = owner_hash_slot(key);
+  while (h->ht[slot] != key) slot = (slot + 1u) & (kOwnSlots - 1);
+  return (h->coll[slot >> 5] >> (slot & 31u)) & 1u;
+}
+
+// Hash phase of the sort-free deposit kernel. lk[0..count) = cell keys (any order). All agents of
+// shared cells go on the short list h->clist (*ncl entries; more than kOwnShared means "crowded":
+// the list is then incomplete). Returns this thread's mask of items (e = t + q * kOwnThreads) that
+// sit in shared cells. The caller has cleared h->ht / h->coll / *ncl and synchronised; ends with a
+// barrier.
 __device__ __forceinline__ unsigned owner_hash_build(int count, const uint32_t* lk, OwnHash* h, int* ncl) {
   const int t = threadIdx.x;
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
     const int e = t + q * kOwnThreads;
-    if (e < count) {
-      const uint32_t key = lk[e];
-      uint32_t slot = (key * 2654435761u) >> (32 - kOwnSlotBits);
-      while (true) {
-        const uint32_t old = atomicCAS(&h->ht[slot], 0xffffffffu, (uint32_t)e);
-        if (old == 0xffffffffu) break;
-        if (lk[old] == key) {  // the slot belongs to this cell already
-          atomicOr(&h->coll[slot >> 5], 1u << (slot & 31u));
-          break;
-        }
-        slot = (slot + 1u) & (kOwnSlots - 1);
-      }
-    }
+    if (e < count) owner_hash_insert(lk[e], h);
   }
   __syncthreads();
   unsigned shared8 = 0u;
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
     const int e = t + q * kOwnThreads;
-    if (e < count) {
-      const uint32_t key = lk[e];
-      uint32_t slot = (key * 2654435761u) >> (32 - kOwnSlotBits);
-      while (lk[h->ht[slot]] != key) slot = (slot + 1u) & (kOwnSlots - 1);  // find the cell's slot again
-      if ((h->coll[slot >> 5] >> (slot & 31u)) & 1u) {
-        shared8 |= 1u << q;
-        const int pos = atomicAdd(ncl, 1);
-        if (pos < kOwnShared) h->clist[pos] = (uint16_t)e;
-      }
+    if (e < count && owner_hash_shared(lk[e], h)) {
+      shared8 |= 1u << q;
+      const int pos = atomicAdd(ncl, 1);
+      if (pos < kOwnShared) h->clist[pos] = (uint16_t)e;
     }
   }
   __syncthreads();

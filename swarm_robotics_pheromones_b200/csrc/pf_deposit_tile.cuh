@@ -107,56 +107,74 @@ k_tile_group(uint32_t* __restrict__ bcnt, const uint32_t* __restrict__ bkey, con
   for (int i = t; i < kOwnSlots; i += kOwnThreads) hs.ht[i] = 0xffffffffu;
   if (t < kOwnSlots / 32) hs.coll[t] = 0u;
   if (t < 32) gcnt[t] = 0u;
-  __syncthreads();  // every thread has read the count
+  __syncthreads();  // every thread has read the count; the hash set is clear
   if (t == 0) {
     bcnt[tile] = 0u;
     ncl = 0;
-    nent = 0u;
     if (raw == 0u) tcount[tile] = 0u;
   }
   if (raw == 0u || raw > (uint32_t)kOwnCap) return;  // empty, or overflowed while binning (flag is set)
   const int count = (int)raw;
+  // records -> shared memory, keys -> hash set, in one phase (the set holds keys, not indices)
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
     const int e = t + q * kOwnThreads;
     if (e < count) {
+      uint32_t k, v, x;
       if (q < kEarly) {
-        lk[e] = k_[q]; lv[e] = v_[q]; le[e] = e_[q];
+        k = k_[q]; v = v_[q]; x = e_[q];
       } else {
-        lk[e] = __ldcs(bkey + base + e);
-        lv[e] = __float_as_uint(__ldcs(bval + base + e));
-        le[e] = __ldcs(bidx + base + e);
+        k = __ldcs(bkey + base + e);
+        v = __float_as_uint(__ldcs(bval + base + e));
+        x = __ldcs(bidx + base + e);
       }
+      lk[e] = k; lv[e] = v; le[e] = x;
+      owner_hash_insert(k, &hs);
     }
   }
   __syncthreads();
-  const unsigned shared8 = owner_hash_build(count, lk, &hs, &ncl);
-  const int nshared = ncl;
-  if (nshared > kOwnShared) {  // crowded tile: leave this tick to the regular deposit kernels
-    if (t == 0) *flag = 1u;
-    return;
-  }
-  // pass 1: every cell's head gets the cell's ordered sum and is counted in its stage group
+  // pass 1a: unshared cells are heads with their own amount: count them per stage group; agents
+  // of shared cells go on the short list
   const int lane = t & 31;
-  unsigned head8 = 0u;
+  unsigned head8 = 0u, shared8 = 0u;
 #pragma unroll
   for (int q = 0; q < kOwnItems; ++q) {
     const int e = t + q * kOwnThreads;
     int g = -1;
     if (e < count) {
-      float s = __uint_as_float(lv[e]);
-      bool head = true;
-      if ((shared8 >> q) & 1u) {
-        head = owner_shared_sum(e, nshared, lk, lv, le, &hs, &s);
-        if (head) lv[e] = __float_as_uint(s);  // read by nobody else: members skip heads
-      }
-      if (head) {
+      const uint32_t key = lk[e];
+      if (owner_hash_shared(key, &hs)) {
+        shared8 |= 1u << q;
+        const int pos = atomicAdd(&ncl, 1);
+        if (pos < kOwnShared) hs.clist[pos] = (uint16_t)e;
+      } else {
         head8 |= 1u << q;
-        g = (int)((lk[e] >> 10) + 2u) / kTileStageRows;
+        g = (int)((key >> 10) + 2u) / kTileStageRows;
       }
     }
     const unsigned peers = __match_any_sync(0xffffffffu, g);
     if (g >= 0 && lane == __ffs(peers) - 1) atomicAdd(&gcnt[g], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  const int nshared = ncl;
+  if (nshared > kOwnShared) {  // crowded tile: leave this tick to the regular deposit kernels
+    if (t == 0) *flag = 1u;
+    return;
+  }
+  // pass 1b: the head of every shared cell gets the cell's ordered sum
+  if (nshared > 0) {  // block-uniform
+#pragma unroll
+    for (int q = 0; q < kOwnItems; ++q) {
+      if ((shared8 >> q) & 1u) {
+        const int e = t + q * kOwnThreads;
+        float s = __uint_as_float(lv[e]);
+        if (owner_shared_sum(e, nshared, lk, lv, le, &hs, &s)) {
+          lv[e] = __float_as_uint(s);  // read by nobody else: members skip heads
+          head8 |= 1u << q;
+          atomicAdd(&gcnt[(int)((lk[e] >> 10) + 2u) / kTileStageRows], 1u);
+        }
+      }
+    }
   }
   __syncthreads();
   unsigned char* blk = tblk + (long long)tile * kTileBlkBytes;
