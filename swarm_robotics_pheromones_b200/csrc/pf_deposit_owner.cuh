@@ -9,12 +9,16 @@
 //   2. k_owner_bounds turns them into a prefix-max / suffix-min pair, so that "every chunk that can
 //      hold a key in [lo, hi)" is a contiguous, binary-searchable chunk range — a guaranteed
 //      superset, however far agents have drifted;
-//   3. k_deposit_owner: each CTA scans its candidate chunks (L2-resident re-reads), compacts the
-//      agents that fall into its key range in ARRAY ORDER, groups them by cell in a shared-memory
-//      hash table, sums each cell's amounts in that order and adds the total to the field — one writer per cell,
-//      no atomics on the field, same summation order as the global-sort path and the oracle.
-//      Ranges holding more than kOwnCap agents are bisected (work stack); a single cell holding more
-//      than kOwnCap agents is summed sequentially.
+//   3. k_deposit_owner: each CTA scans its candidate chunks (L2-resident re-reads), collects the
+//      agents that fall into its key range (any order; the array index travels with the agent),
+//      groups them by cell in a shared-memory hash set, sums each shared cell's amounts in ARRAY
+//      ORDER and adds the total to the field — one writer per cell and kernel, same summation
+//      order as the global-sort path and the oracle. Ranges holding more than kOwnCap agents are
+//      bisected (work stack); a range with more than kOwnShared agents in shared cells is ordered
+//      by one block radix sort instead; a single cell holding more than kOwnCap agents is summed
+//      sequentially.
+// pf_step on one GPU goes one step further and lets the stencil apply the deposits
+// (pf_deposit_tile.cuh); this kernel then only stands by for ticks whose tiles are too crowded.
 #pragma once
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
@@ -252,7 +256,6 @@ __device__ __forceinline__ void owner_group_add(const PFDev& p, uint32_t lo, uin
                                                 OwnScratch* u, int* ncl, float* __restrict__ field,
                                                 const PeerRows& peer) {
   const int t = threadIdx.x;
-  const bool use_red = p.dep_red && !peer.up && !peer.dn;  // mirrored edge rows need the new value
   const unsigned shared8 = owner_hash_build(count, lk, &u->h, ncl);
     const int nshared = *ncl;
 
@@ -327,15 +330,18 @@ __device__ __forceinline__ void owner_group_add(const PFDev& p, uint32_t lo, uin
           }
         }
       }
-      if (use_red) {
+      if (p.dep_red) {
         // one writer per cell and kernel, so a reduction performed by the L2 (no round trip to the
         // SM, no partially written sector) rounds exactly like the load-add-store below. The L2
         // flushes subnormal operands; with every amount >= 1e-30 (p.dep_red) a subnormal cell
-        // value is below half an ulp of the sum either way.
+        // value is below half an ulp of the sum either way. Edge-row cells of an attached strip
+        // need the new value for the neighbour's mailbox and take the load-add-store path.
 #pragma unroll
         for (int q = 0; q < kBatch; ++q)
-          if (cellp[q]) atomicAdd(cellp[q], ssum[q]);
-        continue;
+          if (cellp[q] && !((erow[q] == 0 && peer.up) || (erow[q] == p.rows - 1 && peer.dn))) {
+            atomicAdd(cellp[q], ssum[q]);
+            cellp[q] = nullptr;
+          }
       }
 #pragma unroll
       for (int q = 0; q < kBatch; ++q)
