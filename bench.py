@@ -268,7 +268,9 @@ def measure_other_config(name, steps, sort_every=16):
            "agent_steps_per_s": n / (ms * 1e-3),
            "whole_tick_GBs": (cells * 8 + n * 76 + 8 * min(n, cells)) / (ms * 1e-3) / 1e9}
     if cfg.fsm:
+        from swarm_robotics_pheromones_b200.metrics import NetEnergy
         out["food_grabbed"], out["food_delivered"] = int(c.food_grabbed), int(c.food_delivered)
+        out["net_energy"] = NetEnergy().update(c.food_delivered, c.ticks, n)  # E += F*E_f - E_c (PDF p.19-21)
     f.close()
     return out
 
