@@ -478,7 +478,9 @@ def run_sharded(args):
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = os.environ.get("PF_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL's banner / warnings go to a file
+    os.environ["NCCL_DEBUG"] = os.environ.get("PF_NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pf_nccl_%h_%p.log")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
     scfg = sharded.strip_config(cfg, world, rank, device=local)
@@ -506,14 +508,17 @@ def run_sharded(args):
 
     tick_no = [0]
 
-    def tick():
+    def tick(last=False):
         if args.sort_every > 0 and tick_no[0] % args.sort_every == 0:
             strip.sort_agents()
-        drv.tick(True)
+        # the interior rows' next deposits ride on this tick's stencil (pf_tile_rows) — except on the tick
+        # before a re-sort and on the last tick of a run (the field would hold deposits of a tick not run)
+        before_sort = args.sort_every > 0 and (tick_no[0] + 1) % args.sort_every == 0
+        drv.tick(True, hand_over=not (last or before_sort or args.no_hand_over))
         tick_no[0] += 1
 
-    for _ in range(args.warmup):
-        tick()
+    for k in range(args.warmup):
+        tick(last=k == args.warmup - 1)
     torch.cuda.synchronize()
     dist.barrier()
     tick_no[0] = 0  # the timed region pays ceil(K / sort_every) sorts
@@ -523,8 +528,8 @@ def run_sharded(args):
     sampler.start()
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(args.steps):
-        tick()
+    for k in range(args.steps):
+        tick(last=k == args.steps - 1)
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -652,6 +657,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="sharded run: NCCL send/recv halo instead of peer stores")
     ap.add_argument("--phase-profile", action="store_true", help="sharded run: per-phase CUDA events")
+    ap.add_argument("--no-hand-over", action="store_true",
+                    help="sharded run: always use the separate deposit kernel (no deposits riding on the stencil)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -83,6 +83,8 @@ extern "C" {
 #define PF_STEP_FIELD 0x4u   /* run evaporate(+diffuse)                       algo:354, sup:594 */
 #define PF_STEP_MOVE 0x8u    /* integrate the diff-drive stand-in (Webots physics)              */
 #define PF_STEP_ALL 0xFu
+#define PF_STEP_HANDOVER 0x10u /* pf_agents_step on a strip: robots that end up in the rows of pf_tile_rows hand
+                                  their NEXT deposit to the stencil (see pf_tile_rows)                    */
 
 typedef struct pf_config {
   int32_t abi_version;  /* must be PF_ABI_VERSION */
@@ -318,6 +320,20 @@ int pf_counters_reset(pf_handle* h, void* stream);
 
 /* number of kernels this handle has launched (bench.py reports it as gpu_launches) */
 int pf_launch_count(const pf_handle* h, uint64_t* n);
+
+/* Row strips: deposits riding on the stencil (what pf_step does by itself on one GPU).
+ * [row_begin, row_end) = the local rows whose next-tick deposits the stencil can apply, empty when the
+ * feature is off for this handle (not a strip, no pf_agents_sort yet, stencil variant, ...). They never include
+ * the first 64 rows nor the last 64 next to a neighbour. Protocol per tick, driven by the host:
+ *   pf_agents_deposit            (skips the robots whose deposit the previous tick's stencil applied)
+ *   pf_step_field_rows(1, row_begin)                       before the move kernel, as before
+ *   pf_agents_step(flags | PF_STEP_HANDOVER)               bins + groups the interior rows' deposits
+ *   pf_step_field_rows(row_begin, row_end)                 exactly this range, ONE call: they ride along
+ *   pf_step_field_rows(...) for the remaining rows, pf_swap
+ * After such a tick the rows [row_begin, row_end) already hold the NEXT tick's deposits: do not hand over on
+ * the last tick before reading the field, on the tick before pf_agents_sort (refused), nor if the next tick
+ * will not deposit. */
+int pf_tile_rows(pf_handle* h, const pf_agents* a, int* row_begin, int* row_end);
 
 /* pf_step diagnostics: ticks whose stencil was handed the next tick's deposits, and how many of
  * those fell back on the device to the separate deposit kernels (a tile too crowded).

@@ -37,6 +37,7 @@ OPT_NO_OWNER_DEPOSIT = 4
 OPT_FORCE_OWNER_DEPOSIT = 5
 OPT_NO_TILE_DEPOSIT = 6
 STEP_DEPOSIT, STEP_SENSE, STEP_FIELD, STEP_MOVE, STEP_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
+STEP_HANDOVER = 0x10  # pf_agents_step on a strip: interior rows hand their next deposit to the stencil
 
 # reference constants --------------------------------------------------------------------------
 # Braitenberg coefficients, Phase-3/pheromone_algo_supervisor.py:77

@@ -16,7 +16,12 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
                       const float* __restrict__ y, uint32_t* __restrict__ meta,
                       uint32_t* __restrict__ keys, float* __restrict__ vals, uint32_t sentinel,
                       unsigned long long* __restrict__ counters, uint32_t* __restrict__ cmin,
-                      uint32_t* __restrict__ cmax) {
+                      uint32_t* __restrict__ cmax, TileBins handed, const uint32_t* __restrict__ handed_flag) {
+  // handed.bcnt != null: the last move kernel handed the deposits of the tile rows [ty_lo, ty_hi)
+  // to the stencil (counter already bumped). *handed_flag == 0: the stencil applied them, nothing
+  // left to do for those agents; != 0: it could not (a crowded tile) and they are deposited here
+  // after all, with the amount their bumped counter says.
+  const bool handed_done = handed.bcnt && *handed_flag == 0u;
   // grid-stride over a fixed grid (a multiple of the SM count): the deposit counter costs one
   // global atomic per CTA instead of one per warp (same-address atomics serialise in L2)
   __shared__ unsigned int s_dep;
@@ -31,17 +36,23 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
     uint32_t key = sentinel;
     float amt = 0.0f;
     if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && (mt & PF_META_MOVED)) {
-      uint32_t cnt = (mt >> PF_META_COUNT_SHIFT) + 1u;
-      amt = (st == PF_STATE_SEARCHING)
-                ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
-                : p.i_homing;
-      meta[i] = (mt & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
-      dep = true;
       int r, q;
       bool inside = pf_cell(p, x[i], y[i], r, q);
       int ch = p.dep_ch[st];
-      if (inside && r >= p.row0 && r < p.row1)
-        key = (uint32_t)(((long long)ch * p.rows + (r - p.row0)) * p.W + q);
+      const bool mine = inside && r >= p.row0 && r < p.row1;
+      uint32_t local;
+      const bool was_handed = handed.bcnt && mine && tile_of(handed, ch, r - p.row0, q, &local) >= 0;
+      if (!(was_handed && handed_done)) {
+        uint32_t cnt = (mt >> PF_META_COUNT_SHIFT) + (was_handed ? 0u : 1u);
+        amt = (st == PF_STATE_SEARCHING)
+                  ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
+                  : p.i_homing;
+        if (!was_handed) {
+          meta[i] = (mt & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
+          dep = true;
+        }
+        if (mine) key = (uint32_t)(((long long)ch * p.rows + (r - p.row0)) * p.W + q);
+      }
     }
     keys[i] = key;
     vals[i] = amt;
@@ -370,32 +381,38 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
       awr[i] = wr;
       uint32_t nm = (mt & ~(PF_META_STATE_MASK | PF_META_MOVED | PF_META_DEC_MASK | PF_META_CARRY)) |
                     st | moved | ((uint32_t)dec << PF_META_DEC_SHIFT) | carry;
-      if (next_keys) {
+      if (next_keys || tb.bcnt) {
         // the next tick's deposit rule, evaluated here on the state it would read (identical to
-        // k_deposit_keys_agents; pf_step only asks for it when that deposit is certain to run)
+        // k_deposit_keys_agents; pf_step only asks for it when that deposit is certain to run).
+        // next_keys: every agent's key is written. tb.bcnt: agents whose cell lies in a tile the
+        // stencil takes care of are handed over through the tile's bin (pf_deposit_tile.cuh); on a
+        // strip (no next_keys) the others are left to the next tick's key kernel, untouched.
         uint32_t key = sentinel, local = 0u;
         float amt = 0.0f;
         int tile = -1;
         if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && moved) {
-          uint32_t cnt = (nm >> PF_META_COUNT_SHIFT) + 1u;
-          amt = (st == PF_STATE_SEARCHING) ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
-                                           : p.i_homing;
-          nm = (nm & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
           int r, q;
-          bool inside = pf_cell(p, x, y, r, q);
-          if (inside && r >= p.row0 && r < p.row1) {
-            key = (uint32_t)(((long long)p.dep_ch[st] * p.rows + (r - p.row0)) * p.W + q);
-            if (tb.bcnt) tile = tile_of(tb, p.dep_ch[st], r - p.row0, q, &local);
+          const bool inside = pf_cell(p, x, y, r, q);
+          const bool mine = inside && r >= p.row0 && r < p.row1;
+          if (mine && tb.bcnt) tile = tile_of(tb, p.dep_ch[st], r - p.row0, q, &local);
+          if (next_keys || tile >= 0) {
+            uint32_t cnt = (nm >> PF_META_COUNT_SHIFT) + 1u;
+            amt = (st == PF_STATE_SEARCHING) ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
+                                             : p.i_homing;
+            nm = (nm & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
+            if (mine) key = (uint32_t)(((long long)p.dep_ch[st] * p.rows + (r - p.row0)) * p.W + q);
+            atomicAdd(&hist[8], 1u);
           }
-          atomicAdd(&hist[8], 1u);
         }
-        next_keys[i] = key;
-        next_vals[i] = amt;
-        if (tb.bcnt) tile_bin_put(tb, __activemask(), tile, local, amt, (uint32_t)i);  // pf_deposit_tile.cuh
-        if (cmin) {
-          const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
-          owner_note_bounds(cmin, cmax, i / kOwnChunk, key % plane, key != sentinel);
+        if (next_keys) {
+          next_keys[i] = key;
+          next_vals[i] = amt;
+          if (cmin) {
+            const uint32_t plane = (uint32_t)((long long)p.rows * p.W);
+            owner_note_bounds(cmin, cmax, i / kOwnChunk, key % plane, key != sentinel);
+          }
         }
+        if (tb.bcnt) tile_bin_put(tb, __activemask(), tile, local, amt, (uint32_t)i);
       }
       ameta[i] = nm;
       if (dec_out) dec_out[i] = (uint8_t)dec;

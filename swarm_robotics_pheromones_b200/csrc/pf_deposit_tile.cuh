@@ -50,6 +50,8 @@ struct TileBins {
   uint32_t* bidx;
   uint32_t* flag;
   int nx, ny;      // tiles along a row / along a column of one channel plane
+  int ty_lo, ty_hi;  // tile rows whose deposits the stencil takes (all of them on one GPU; on a strip
+                     // the interior ones that the stencil writes after the move kernel)
 };
 
 // Called by every thread of `act` (converged); tile < 0 = nothing to put. One counter update per
@@ -75,9 +77,11 @@ __device__ __forceinline__ void tile_bin_put(const TileBins& tb, unsigned act, i
   }
 }
 
-// tile and cell-within-tile of (channel, strip-local row, column)
+// tile and cell-within-tile of (channel, strip-local row, column); -1 if the stencil does not take
+// that tile row's deposits
 __device__ __forceinline__ int tile_of(const TileBins& tb, int ch, int lr, int col, uint32_t* local) {
   const int ty = lr / kTileRows, tx = col / kTileCols;
+  if (ty < tb.ty_lo || ty >= tb.ty_hi) return -1;
   *local = (uint32_t)((lr - ty * kTileRows) * kTileCols + (col - tx * kTileCols));
   return (ch * tb.ny + ty) * tb.nx + tx;
 }

@@ -32,6 +32,7 @@ struct StencilArgs {
   const uint32_t* dep_flag;   // != 0: lists are not usable this tick
   const uint32_t* dep_count;  // [tile] entries
   const unsigned char* dep_blk;  // [tile] start[] / col[] / sum[] block
+  int dep_ty0, dep_ny;           // tile row of this launch's first CTA row; tile rows per channel
 };
 
 // per-channel constant without dynamic indexing of the kernel parameter block (which would make

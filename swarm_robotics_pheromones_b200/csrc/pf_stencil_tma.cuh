@@ -105,7 +105,7 @@ k_stencil_tma(StencilArgs a) {
   uint32_t ndep = 0u;
   long long tile = 0;
   if (DEP) {
-    tile = ((long long)ch * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    tile = ((long long)ch * a.dep_ny + a.dep_ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
     if (*a.dep_flag == 0u) ndep = a.dep_count[tile];  // uniform per CTA
   }
   if (threadIdx.x == 0) {
@@ -308,14 +308,19 @@ static int tma_stencil_launch(TmaStencilState* st, int shape, const pf_config& c
 #undef PF_TMA_DISPATCH
 }
 
-// Whole-field launch with the next tick's deposits riding along: CTA = deposit tile (kDepRows rows x
-// kTmaCols columns x one channel), ring shape 4 x 4. The caller has checked W % 4 == 0, W >= 128,
-// stencil != 0, no peers.
-static int tma_stencil_launch_dep(TmaStencilState* st, const PFDev& d, StencilArgs a, cudaStream_t s) {
-  a.r_begin = 0;
-  a.r_end = d.rows;
+// Launch over the tile rows [ty0, ty1) with the next tick's deposits riding along: CTA = deposit tile
+// (kDepRows rows x kTmaCols columns x one channel), ring shape 4 x 4. The caller has checked
+// W % 4 == 0, W >= 128, stencil != 0; the rows are interior ones on a strip (no peer stores).
+static int tma_stencil_launch_dep(TmaStencilState* st, const PFDev& d, StencilArgs a, int ty0, int ty1,
+                                  cudaStream_t s) {
+  a.r_begin = ty0 * kDepRows;
+  a.r_end = ty1 * kDepRows < d.rows ? ty1 * kDepRows : d.rows;
   a.rows_per_cta = kDepRows;
-  dim3 grid((d.W + kTmaCols - 1) / kTmaCols, (d.rows + kDepRows - 1) / kDepRows, d.C);
+  a.dep_ty0 = ty0;
+  a.dep_ny = (d.rows + kDepRows - 1) / kDepRows;
+  a.peer.up = nullptr;
+  a.peer.dn = nullptr;
+  dim3 grid((d.W + kTmaCols - 1) / kTmaCols, ty1 - ty0, d.C);
   if (d.stencil == 5) return tma_launch_one<5, 4, 4, false, true>(st, 8, a, grid, s);
   return tma_launch_one<9, 4, 4, false, true>(st, 8, a, grid, s);
 }

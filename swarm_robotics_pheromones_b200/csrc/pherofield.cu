@@ -66,7 +66,9 @@ struct pf_handle {
   unsigned char* tile_blk;
   long long tile_alloc;   // tiles allocated
   int no_tile_deposit;
-  bool tile_pending;      // the last stencil launch was asked to apply the next tick's deposits
+  bool tile_pending;      // lists are ready for (pf_step: were given to) the stencil launch over tile_ty0..ty1
+  bool tile_handed;       // strips: that launch has happened; the next pf_agents_deposit skips those agents
+  int tile_ty0, tile_ty1; // tile rows handed over
   unsigned long long tile_attempts, g_tile_attempts;
   long long own_alloc;      // chunks allocated
   long long own_n;          // agent slots the splitters were built for (0 = invalid)
@@ -529,10 +531,10 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, 
   for (int k = 0; k < PF_MAX_CHANNELS; ++k) { a.keep[k] = d.keep[k]; a.dk[k] = d.dk[k]; }
   a.del_thr = d.del_thr;
   a.peer = peer_rows(h, h->cur ^ 1);
-  a.dep_flag = nullptr; a.dep_count = nullptr; a.dep_blk = nullptr;
-  if (with_deposits) {  // tile_ok() holds: whole field, TMA ring, CTA = deposit tile
+  a.dep_flag = nullptr; a.dep_count = nullptr; a.dep_blk = nullptr; a.dep_ty0 = 0; a.dep_ny = 0;
+  if (with_deposits) {  // tile_ok() / strip_tile_range() hold: whole tile rows, TMA ring, CTA = deposit tile
     a.dep_flag = h->tile_flag; a.dep_count = h->tile_count; a.dep_blk = h->tile_blk;
-    int rc = tma_stencil_launch_dep(&h->tma, d, a, s);
+    int rc = tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, h->tile_ty1, s);
     if (rc != PF_OK) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
     h->launches++;
     return PF_OK;
@@ -601,11 +603,23 @@ extern "C" int pf_step_field(pf_handle* h, int nsteps, void* stream) {
 extern "C" int pf_step_field_rows(pf_handle* h, int row_begin, int row_end, void* stream) {
   if (!h || row_begin < 0 || row_end > h->dev.rows) return PF_EINVAL;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (h->tile_pending && is_sharded(h) && row_begin == h->tile_ty0 * kTileRows &&
+      row_end == (h->tile_ty1 * kTileRows < h->dev.rows ? h->tile_ty1 * kTileRows : h->dev.rows)) {
+    // the rows whose next-tick deposits pf_agents_step(PF_STEP_HANDOVER) has prepared: they ride along
+    int rc = launch_stencil(h, row_begin, row_end, (cudaStream_t)stream, true);
+    if (rc) return rc;
+    h->tile_pending = false;
+    h->tile_handed = true;
+    return PF_OK;
+  }
   return launch_stencil(h, row_begin, row_end, (cudaStream_t)stream);
 }
 
 extern "C" int pf_swap(pf_handle* h) {
   if (!h) return PF_EINVAL;
+  if (h->tile_pending)
+    return set_err(h, PF_ESTATE, "pf_swap: deposits were handed over (PF_STEP_HANDOVER) but the rows of pf_tile_rows "
+                                 "were not stepped as one pf_step_field_rows call");
   h->cur ^= 1;
   return PF_OK;
 }
@@ -632,6 +646,7 @@ extern "C" int pf_set_stencil_variant(pf_handle* h, int variant, int rows_per_ct
 // K2 launch
 // ---------------------------------------------------------------------------------------------
 static bool owner_ready(const pf_handle* h, const pf_agents* a);
+static int check_agents(pf_handle* h, const pf_agents* a);
 
 extern "C" int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_back) {
   if (!h) return PF_EINVAL;
@@ -649,17 +664,48 @@ extern "C" int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_b
 // Can this tick's stencil apply the next tick's deposits (pf_deposit_tile.cuh)? Needs the sort-free
 // deposit (its kernels are the device-side fallback), the TMA stencil in its default shape on the
 // whole field, and no second stream.
-static bool tile_ok(const pf_handle* h, const pf_agents* a) {
+static bool tile_common_ok(const pf_handle* h, const pf_agents* a) {
   const PFDev& d = h->dev;
-  return !h->no_tile_deposit && !is_sharded(h) && !h->overlap_agents && owner_ready(h, a) && d.stencil != 0 &&
-         d.dep_red &&
+  return !h->no_tile_deposit && !h->overlap_agents && owner_ready(h, a) && d.stencil != 0 && d.dep_red &&
          d.W % 4 == 0 && d.W >= 512 && (h->variant == 0 || h->variant == 2) && h->rows_per_cta <= 0 &&
          kTileRows == kDepRows && kTileEnt == kDepEnt && kTileCols == kTmaCols && kTileBlkBytes == kDepBlkBytes &&
          kTilePtrBytes == kDepPtrBytes;
 }
+static bool tile_ok(const pf_handle* h, const pf_agents* a) { return !is_sharded(h) && tile_common_ok(h, a); }
+
+// Strips: the tile rows [ty0, ty1) whose next-tick deposits the stencil can take. Not the first
+// tile rows (the driver steps them before the move kernel, to hide the halo exchange: an eighth of
+// the strip, at least 64 rows) and not the last 64+ rows next to a neighbour: arrivals land in the
+// edge bands (a robot moves well under 32 cells per tick — checked), so no handed-over cell is
+// shared with an agent the regular deposit kernel handles.
+static bool strip_tile_range(const pf_handle* h, const pf_agents* a, int* ty0, int* ty1) {
+  *ty0 = *ty1 = 0;
+  if (!is_sharded(h) || !tile_common_ok(h, a)) return false;
+  const PFDev& d = h->dev;
+  const double omega = fabs((double)d.vmax) + fabs((double)d.cruise) + fabs((double)d.bl) + fabs((double)d.br);
+  const double step_cells = omega * h->cfg.wheel_radius * h->cfg.dt / h->cfg.cell_size;
+  if (!(step_cells < 32.0)) return false;
+  const int rows = h->dev.rows, ny = (rows + kTileRows - 1) / kTileRows;
+  int lo = ny / 8 > 1 ? ny / 8 : 1;
+  int hi = (h->cfg.row1 < h->cfg.H) ? (rows - kTileRows) / kTileRows : ny;
+  if (hi <= lo) return false;
+  *ty0 = lo;
+  *ty1 = hi;
+  return true;
+}
+
+extern "C" int pf_tile_rows(pf_handle* h, const pf_agents* a, int* row_begin, int* row_end) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  int ty0, ty1;
+  strip_tile_range(h, a, &ty0, &ty1);
+  if (row_begin) *row_begin = ty0 * kTileRows;
+  if (row_end) *row_end = ty1 * kTileRows < h->dev.rows ? ty1 * kTileRows : h->dev.rows;
+  return PF_OK;
+}
 
 // before the move kernel: storage, cleared status flag, the bins the kernel fills
-static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb) {
+static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb, int ty0, int ty1) {
   const int nx = (h->dev.W + kTileCols - 1) / kTileCols, ny = (h->dev.rows + kTileRows - 1) / kTileRows;
   const long long ntiles = (long long)nx * ny * h->dev.C;
   if (h->tile_alloc < ntiles) {
@@ -677,7 +723,9 @@ static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb) {
   }
   PF_CUDA(h, cudaMemsetAsync(h->tile_flag, 0, sizeof(uint32_t), s));
   tb->bcnt = h->tile_bcnt; tb->bkey = h->tile_bkey; tb->bval = h->tile_bval; tb->bidx = h->tile_bidx;
-  tb->flag = h->tile_flag; tb->nx = nx; tb->ny = ny;
+  tb->flag = h->tile_flag; tb->nx = nx; tb->ny = ny; tb->ty_lo = ty0; tb->ty_hi = ty1;
+  h->tile_ty0 = ty0;
+  h->tile_ty1 = ty1;
   return PF_OK;
 }
 
@@ -767,10 +815,20 @@ extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream)
   uint32_t* keys_in = (uint32_t*)h->scratch;
   float* vals_in = (float*)(keys_in + 2 * h->cap);
   const bool own = owner_ready(h, a);
+  TileBins handed;
+  memset(&handed, 0, sizeof(handed));
+  if (h->tile_handed) {  // the last stencil took the interior tile rows' deposits (unless its flag says otherwise)
+    handed.bcnt = h->tile_bcnt;
+    handed.nx = (h->dev.W + kTileCols - 1) / kTileCols;
+    handed.ny = (h->dev.rows + kTileRows - 1) / kTileRows;
+    handed.ty_lo = h->tile_ty0;
+    handed.ty_hi = h->tile_ty1;
+    h->tile_handed = false;
+  }
   k_deposit_keys_agents<<<wave_grid(a->n, h->wave_keys), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, keys_in,
                                                              vals_in, h->sentinel, h->counters,
                                                              own ? h->own_cmin : nullptr,
-                                                             own ? h->own_cmax : nullptr);
+                                                             own ? h->own_cmax : nullptr, handed, h->tile_flag);
   PF_LAUNCH_CHECK(h);
   return own ? owner_sum(h, a->n, s) : sort_and_sum(h, a->n, s);
 }
@@ -812,7 +870,7 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
                                                      nk, nv, h->sentinel,
                                                      (nk && owner_ready(h, a)) ? h->own_cmin : nullptr,
                                                      (nk && owner_ready(h, a)) ? h->own_cmax : nullptr,
-                                                     (nk && bins) ? *bins : no_bins);
+                                                     bins ? *bins : no_bins);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -823,7 +881,24 @@ extern "C" int pf_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
   if (rc) return rc;
   if (a->n == 0) return PF_OK;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
-  return launch_agents_step(h, a, flags, decisions_out, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  int ty0, ty1;
+  if ((flags & PF_STEP_HANDOVER) && (flags & PF_STEP_MOVE) && strip_tile_range(h, a, &ty0, &ty1)) {
+    // strips: the agents that end up in the interior tile rows hand their next deposit to the stencil
+    rc = pf_reserve_agents(h, a->n);
+    if (rc) return rc;
+    TileBins bins;
+    rc = tile_begin(h, s, &bins, ty0, ty1);
+    if (rc) return rc;
+    rc = launch_agents_step(h, a, flags & ~PF_STEP_HANDOVER, decisions_out, s, false, &bins);
+    if (rc) return rc;
+    rc = tile_finish(h, s);
+    if (rc) return rc;
+    h->tile_pending = true;
+    h->tile_attempts++;
+    return PF_OK;
+  }
+  return launch_agents_step(h, a, flags & ~PF_STEP_HANDOVER, decisions_out, s);
 }
 
 extern "C" int pf_set_time(pf_handle* h, double time_s, double start_delay_s) {
@@ -952,7 +1027,7 @@ static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream
     const bool tile_try = emit && (mask & PF_STEP_FIELD) && tile_ok(h, a);
     TileBins bins;
     if (tile_try) {
-      rc = tile_begin(h, as, &bins);
+      rc = tile_begin(h, as, &bins, 0, (h->dev.rows + kTileRows - 1) / kTileRows);
       if (rc) return rc;
     }
     rc = launch_agents_step(h, a, flags, nullptr, as, emit, tile_try ? &bins : nullptr);
@@ -1092,6 +1167,10 @@ extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
   int rc = check_agents(h, a);
   if (rc) return rc;
   if (a->n <= 1) return PF_OK;
+  if (h->tile_handed || h->tile_pending)
+    return set_err(h, PF_ESTATE, "pf_agents_sort between a hand-over tick (PF_STEP_HANDOVER) and the next deposit: "
+                                 "shared cells were summed in the old array order; do not hand over on the tick "
+                                 "before a re-sort");
   rc = pf_reserve_agents(h, a->n);
   if (rc) return rc;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));

@@ -294,6 +294,12 @@ class PheroField:
         self._ck(self._L.pf_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def tile_rows(self, swarm):
+        """strips: local rows whose next-tick deposits the stencil can take (pf_tile_rows); (0, 0) = none"""
+        r0, r1 = C.c_int(), C.c_int()
+        self._ck(self._L.pf_tile_rows(self._h, C.byref(swarm.struct()), C.byref(r0), C.byref(r1)))
+        return r0.value, r1.value
+
     def tile_stats(self):
         """(ticks whose stencil carried the next tick's deposits, how many of them fell back)"""
         a, f = C.c_uint64(), C.c_uint64()

@@ -101,6 +101,10 @@ class CudaStrip:
     def agents(self, flags):
         self.field.agents_step(self.swarm, flags)
 
+    def tile_rows(self):
+        """local rows whose next-tick deposits the stencil can apply (pf_tile_rows); (0, 0) = none"""
+        return self.field.tile_rows(self.swarm)
+
     def swap(self):
         self.field.swap()
         if getattr(self, "_cache", None) is not None:
@@ -199,6 +203,16 @@ class StripWorker:
             out.append((self.rank + 1, bottom))
         return out
 
+    # Deposits riding on the stencil (what pf_step does by itself on one GPU): the move kernel hands
+    # the next deposit of the robots in the interior rows `dep` to the stencil launch over exactly
+    # those rows. hand_over=False on the tick before a re-sort, or if the next tick does not deposit.
+    dep = (0, 0)
+
+    def begin_tick(self, hand_over: bool = True):
+        self.dep = (0, 0)
+        if hand_over and hasattr(self.b, "tile_rows"):
+            self.dep = tuple(self.b.tile_rows())
+
     # phase 3: the stencil is split so that both exchanges hide behind it —
     #   interior part A  (while the halo is in flight)
     #   agents           (needs the ghost rows; produces the leavers)
@@ -206,6 +220,8 @@ class StripWorker:
     def _split(self):
         rows = self.b.rows
         lo, hi = 1, max(1, rows - 1)
+        if self.dep[1] > self.dep[0]:
+            return lo, self.dep[0], hi
         return lo, lo + (hi - lo) // 2, hi
 
     def field_interior_a(self):
@@ -214,15 +230,27 @@ class StripWorker:
             self.b.field_rows(lo, mid)
 
     def agents(self, sense_enabled: bool, move: bool = True):
-        self.b.agents(self.flags(sense_enabled, move))
+        flags = self.flags(sense_enabled, move)
+        if self.dep[1] > self.dep[0] and sense_enabled and move:
+            flags |= abi.STEP_HANDOVER
+        else:
+            self.dep = (0, 0)
+        self.b.agents(flags)
 
     def field_rest(self):
         rows = self.b.rows
         _, mid, hi = self._split()
-        if hi > mid:
+        last_done = False
+        if self.dep[1] > self.dep[0]:
+            d0, d1 = self.dep
+            self.b.field_rows(d0, d1)          # ONE call over exactly these rows: the deposits ride along
+            last_done = d1 >= rows              # arena edge below: the range runs to the last row
+            if hi > d1:
+                self.b.field_rows(d1, hi)
+        elif hi > mid:
             self.b.field_rows(mid, hi)
         self.b.field_rows(0, min(1, rows))
-        if rows > 1:
+        if rows > 1 and not last_done:
             self.b.field_rows(rows - 1, rows)
         self.b.swap()
 
@@ -284,8 +312,9 @@ class LocalDriver:
 
     peer = False
 
-    def tick(self, sense_enabled: bool = True):
+    def tick(self, sense_enabled: bool = True, hand_over: bool = True):
         for w in self.w:
+            w.begin_tick(hand_over and sense_enabled)
             w.deposit(sense_enabled)
             if self.peer:
                 w.b.peer_signal()
@@ -348,9 +377,11 @@ class DistDriver:
                 r.wait()
             ev_after.record(self.comm_stream)
 
-    def tick(self, sense_enabled: bool = True, move: bool = True):
-        """move=False: the caller owns the poses (pf_agents_observe); nothing migrates"""
+    def tick(self, sense_enabled: bool = True, move: bool = True, hand_over: bool = True):
+        """move=False: the caller owns the poses (pf_agents_observe); nothing migrates.
+        hand_over=False: on the tick before a re-sort (pf_agents_sort) or before a tick without deposit"""
         w = self.w
+        w.begin_tick(hand_over and sense_enabled and move)
         marks = [] if (self.profile and self.cuda) else None
 
         def mark(label):

@@ -50,3 +50,47 @@ def test_strips_equal_unsharded_bitexact(world, variant, peer):
     assert sum(w.b.field.counters().migrate_dropped for w in workers) == 0
     for w in workers:
         w.b.field.close()
+
+
+@pytest.mark.parametrize("peer", [False, True])
+@pytest.mark.parametrize("world", [2, 3])
+def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
+    # strips tall enough to have interior tile rows (64 rows x 1024 columns): the move kernel hands the
+    # next deposit of the robots there to the stencil (PF_STEP_HANDOVER), the edge bands and the
+    # arrivals keep the separate deposit kernel; both with and without peer-store halos
+    cfg, x, y, th, st = _scenario(seed=21, n=14000, H=768, W=512, C=2)
+    nticks = 40
+    o = dense.DenseOracle(cfg)
+    a = dense.AgentsNP(x, y, th, st)
+    o.tick(a, nticks)
+    parts = sharded.partition_agents(cfg, world, x, y, th, st)
+    workers = []
+    for r in range(world):
+        p = parts[r]
+        strip = sharded.CudaStrip(sharded.strip_config(cfg, world, r), p["x"], p["y"], p["theta"],
+                                  p["state"], p["gid"], capacity=14000, migrate_cap=1024)
+        strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)  # 4-7 k robots per strip: below the default threshold
+        workers.append(sharded.StripWorker(strip, r, world))
+    drv = sharded.LocalDriver(workers)
+    if peer:
+        drv.attach_peers()
+    for t in range(nticks):
+        if t % 16 == 0:
+            for w in workers:
+                w.b.sort_agents()
+        # not on the tick before a re-sort, nor on the last one: after a hand-over tick the interior
+        # rows already hold the NEXT tick's deposits
+        drv.tick(True, hand_over=(t + 1) % 16 != 0 and t != nticks - 1)
+    torch.cuda.synchronize()
+    field = np.concatenate([w.b.field.snapshot() for w in workers], axis=1)
+    assert (field.view(np.uint32) == np.ascontiguousarray(o.field).view(np.uint32)).all()
+    got = gather_agents_sorted([w.b.swarm.to_numpy() for w in workers])
+    assert len(got["gid"]) == a.n
+    for f in dense.AgentsNP.FIELDS:
+        assert (got[f].view(np.uint32) == getattr(a, f).view(np.uint32)).all(), f
+    assert sum(w.b.field.counters().migrated_out for w in workers) > 0
+    assert sum(w.b.field.counters().deposits for w in workers) == int(o.counters[8])
+    for w in workers:
+        attempted, fell_back = w.b.field.tile_stats()
+        assert attempted == nticks - 3 and fell_back == 0, (w.rank, attempted, fell_back)
+        w.b.field.close()

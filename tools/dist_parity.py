@@ -23,6 +23,7 @@ ap.add_argument("--grid", type=int, default=2048)
 ap.add_argument("--agents", type=int, default=200000)
 ap.add_argument("--no-overlap", action="store_true")
 ap.add_argument("--sort-every", type=int, default=16)
+ap.add_argument("--no-hand-over", action="store_true")
 ap.add_argument("--peer", action="store_true", help="peer-store halo (CUDA IPC + NVLink P2P) instead of NCCL")
 args = ap.parse_args()
 
@@ -62,7 +63,9 @@ if args.peer:
 for t in range(args.ticks):
     if args.sort_every and t % args.sort_every == 0:
         strip.sort_agents()
-    drv.tick(True)
+    # interior rows hand their next deposit to the stencil, except before a re-sort and on the last tick
+    before_sort = args.sort_every and (t + 1) % args.sort_every == 0
+    drv.tick(True, hand_over=not (before_sort or t == args.ticks - 1 or args.no_hand_over))
 torch.cuda.synchronize()
 
 # gather strips on rank 0
@@ -102,7 +105,8 @@ if rank == 0:
         for k, f in enumerate(("x", "y", "theta", "wl", "wr", "meta")))
     mig = strip.field.counters()
     ok = same_field and same_agents
-    print(f"dist_parity world={world} peer_halo={args.peer} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
+    att, fb = strip.field.tile_stats()
+    print(f"dist_parity world={world} hand-over ticks on rank 0: {att} (fell back {fb}); peer_halo={args.peer} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
           f"agents_bitexact={same_agents} (rank0 migrated_out={mig.migrated_out}, dropped={mig.migrate_dropped}) "
           f"-> {'PASS' if ok else 'FAIL'}", flush=True)
 else:
