@@ -234,7 +234,7 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
               float* __restrict__ ax, float* __restrict__ ay, float* __restrict__ ath,
               float* __restrict__ awl, float* __restrict__ awr, uint32_t* __restrict__ ameta,
               uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters,
-              unsigned long long* __restrict__ mig_flags, uint32_t* __restrict__ next_keys,
+              uint32_t* __restrict__ mig_cnt, uint32_t* __restrict__ next_keys,
               float* __restrict__ next_vals, uint32_t sentinel, uint32_t* __restrict__ cmin,
               uint32_t* __restrict__ cmax, TileBins tb) {
   __shared__ unsigned int hist[9];  // 0..5 decisions, 6 grabbed, 7 delivered, 8 deposits (next tick)
@@ -247,7 +247,6 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
     uint32_t st = mt & PF_META_STATE_MASK;
     if (st == PF_STATE_EMPTY) {
       if (dec_out) dec_out[i] = PF_DEC_NONE;
-      if (mig_flags) mig_flags[i] = 0ull;
       if (next_keys) { next_keys[i] = sentinel; next_vals[i] = 0.0f; }
     } else {
       float x = ax[i], y = ay[i], th = ath[i], wl = awl[i], wr = awr[i];
@@ -416,10 +415,11 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
       }
       ameta[i] = nm;
       if (dec_out) dec_out[i] = (uint8_t)dec;
-      if (mig_flags) {  // same rule as k_migrate_flags: did the (new) cell row leave the strip?
+      if (mig_cnt) {  // same rule as mig_leaves: did the (new) cell row leave the strip? (rare: one atomic each)
         int r, q;
         pf_cell(p, x, y, r, q);
-        mig_flags[i] = (r < p.row0) ? 1ull : ((r >= p.row1) ? (1ull << 32) : 0ull);
+        if (r < p.row0) atomicAdd(&mig_cnt[2 * (i / kOwnChunk)], 1u);
+        else if (r >= p.row1) atomicAdd(&mig_cnt[2 * (i / kOwnChunk) + 1], 1u);
       }
     }
   }
@@ -457,56 +457,109 @@ k_agents_observe(PFDev p, long long n, float* __restrict__ ax, float* __restrict
 // ------------------------------------------------------------------------------------------
 constexpr int kMigWords = 8;  // u32 words per record and per header
 
-__global__ void __launch_bounds__(256)
-k_migrate_flags(PFDev p, long long n, const float* __restrict__ x, const float* __restrict__ y,
-                const uint32_t* __restrict__ meta, unsigned long long* __restrict__ flags) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  unsigned long long fl = 0ull;
-  if ((meta[i] & PF_META_STATE_MASK) != PF_STATE_EMPTY) {
-    int r, q;
-    pf_cell(p, x[i], y[i], r, q);
-    if (r < p.row0) fl = 1ull;
-    else if (r >= p.row1) fl = 1ull << 32;
-  }
-  flags[i] = fl;
+// Two-level migration. Leavers and free slots are a few thousand out of millions, so nothing here
+// makes a full-array scan: per 1024-slot chunk counts (the move kernel counts leavers with one
+// atomic each), one small scan over the chunks, and detail work only in the chunks that need it.
+// Order is deterministic: leavers are packed by slot; arrivals take free slots by candidate rank.
+
+// 0 = stays, 1 = leaves upwards, 2 = leaves downwards
+__device__ __forceinline__ int mig_leaves(const PFDev& p, float x, float y, uint32_t meta) {
+  if ((meta & PF_META_STATE_MASK) == PF_STATE_EMPTY) return 0;
+  int r, q;
+  pf_cell(p, x, y, r, q);
+  return (r < p.row0) ? 1 : ((r >= p.row1) ? 2 : 0);
 }
 
+// leaver counts per chunk, for callers that moved the agents themselves (the move kernel counts on its own)
 __global__ void __launch_bounds__(256)
-k_migrate_scatter(long long n, long long cap, const unsigned long long* __restrict__ flags,
-                  const unsigned long long* __restrict__ ranks, float* ax, float* ay, float* ath,
-                  float* awl, float* awr, uint32_t* ameta, const uint32_t* __restrict__ agid,
-                  uint32_t* __restrict__ up, uint32_t* __restrict__ down,
-                  unsigned long long* __restrict__ counters) {
+k_migrate_count(PFDev p, long long n, const float* __restrict__ x, const float* __restrict__ y,
+                const uint32_t* __restrict__ meta, uint32_t* __restrict__ mig_cnt) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long fl = flags[i], rk = ranks[i];
-  if (i == n - 1) {  // totals -> headers
-    unsigned long long tot = rk + fl;
-    unsigned long long nu = tot & 0xffffffffull, nd = tot >> 32;
-    unsigned long long su = nu < (unsigned long long)cap ? nu : cap;
-    unsigned long long sd = nd < (unsigned long long)cap ? nd : cap;
+  const int lv = mig_leaves(p, x[i], y[i], meta[i]);
+  if (lv) atomicAdd(&mig_cnt[2 * (i / kOwnChunk) + (lv - 1)], 1u);
+}
+
+// exclusive scan of `cnt[stride * c + off]` over c < nc into base[]; one CTA of 1024 threads; returns the total
+__device__ __forceinline__ uint32_t mig_chunk_scan(const uint32_t* __restrict__ cnt, int stride, int off, int nc,
+                                                   uint32_t* __restrict__ base, uint32_t* carry_smem, void* tmp_) {
+  typedef cub::BlockScan<uint32_t, 1024> Scan;
+  typename Scan::TempStorage& tmp = *reinterpret_cast<typename Scan::TempStorage*>(tmp_);
+  if (threadIdx.x == 0) *carry_smem = 0u;
+  __syncthreads();
+  for (int b0 = 0; b0 < nc; b0 += 1024) {
+    const int c = b0 + threadIdx.x;
+    const uint32_t v = c < nc ? cnt[stride * c + off] : 0u;
+    uint32_t ex, total;
+    Scan(tmp).ExclusiveSum(v, ex, total);
+    const uint32_t carry = *carry_smem;
+    if (c < nc) base[stride * c + off] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) *carry_smem = carry + total;
+    __syncthreads();
+  }
+  return *carry_smem;
+}
+
+// headers of the two record buffers + counters; mig_base = first record index of each chunk's leavers
+__global__ void __launch_bounds__(1024)
+k_migrate_offsets(int nc, long long cap, const uint32_t* __restrict__ mig_cnt, uint32_t* __restrict__ mig_base,
+                  uint32_t* __restrict__ up, uint32_t* __restrict__ down,
+                  unsigned long long* __restrict__ counters) {
+  __shared__ typename cub::BlockScan<uint32_t, 1024>::TempStorage tmp;
+  __shared__ uint32_t carry;
+  const unsigned long long nu = mig_chunk_scan(mig_cnt, 2, 0, nc, mig_base, &carry, &tmp);
+  __syncthreads();
+  const unsigned long long nd = mig_chunk_scan(mig_cnt, 2, 1, nc, mig_base, &carry, &tmp);
+  if (threadIdx.x == 0) {
+    const unsigned long long su = nu < (unsigned long long)cap ? nu : cap;
+    const unsigned long long sd = nd < (unsigned long long)cap ? nd : cap;
     up[0] = (uint32_t)su;
     down[0] = (uint32_t)sd;
     atomicAdd(&counters[10], su + sd);
     if (nu + nd > su + sd) atomicAdd(&counters[12], nu + nd - su - sd);
   }
-  if (!fl) return;
-  uint32_t* dst;
-  unsigned long long r;
-  if (fl & 0xffffffffull) { dst = up; r = rk & 0xffffffffull; }
-  else { dst = down; r = rk >> 32; }
-  if (r >= (unsigned long long)cap) return;  // overflow: stays here, retried next tick
-  uint32_t* rec = dst + (r + 1) * kMigWords;
-  rec[0] = __float_as_uint(ax[i]);
-  rec[1] = __float_as_uint(ay[i]);
-  rec[2] = __float_as_uint(ath[i]);
-  rec[3] = __float_as_uint(awl[i]);
-  rec[4] = __float_as_uint(awr[i]);
-  rec[5] = ameta[i];
-  rec[6] = agid ? agid[i] : 0u;
-  rec[7] = 0u;
-  ameta[i] = PF_STATE_EMPTY;
+}
+
+// one CTA per chunk; chunks without leavers return at once. Records are written in slot order.
+__global__ void __launch_bounds__(256)
+k_migrate_scatter(PFDev p, long long n, long long cap, const uint32_t* __restrict__ mig_cnt,
+                  const uint32_t* __restrict__ mig_base, float* ax, float* ay, float* ath, float* awl, float* awr,
+                  uint32_t* ameta, const uint32_t* __restrict__ agid, uint32_t* __restrict__ up,
+                  uint32_t* __restrict__ down) {
+  const int c = blockIdx.x;
+  if (mig_cnt[2 * c] == 0u && mig_cnt[2 * c + 1] == 0u) return;
+  typedef cub::BlockScan<unsigned long long, 256> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  const long long i0 = (long long)c * kOwnChunk + 4 * threadIdx.x;
+  int lv[4];
+  unsigned long long mine = 0ull;  // leavers of this thread: up in the low word, down in the high word
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long i = i0 + q;
+    lv[q] = i < n ? mig_leaves(p, ax[i], ay[i], ameta[i]) : 0;
+    mine += lv[q] == 1 ? 1ull : (lv[q] == 2 ? (1ull << 32) : 0ull);
+  }
+  unsigned long long ex;
+  Scan(tmp).ExclusiveSum(mine, ex);
+  unsigned long long ru = mig_base[2 * c] + (ex & 0xffffffffull), rd = mig_base[2 * c + 1] + (ex >> 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (!lv[q]) continue;
+    const long long i = i0 + q;
+    const unsigned long long r = lv[q] == 1 ? ru++ : rd++;
+    if (r >= (unsigned long long)cap) continue;  // overflow: stays here, retried next tick
+    uint32_t* rec = (lv[q] == 1 ? up : down) + (r + 1) * kMigWords;
+    rec[0] = __float_as_uint(ax[i]);
+    rec[1] = __float_as_uint(ay[i]);
+    rec[2] = __float_as_uint(ath[i]);
+    rec[3] = __float_as_uint(awl[i]);
+    rec[4] = __float_as_uint(awr[i]);
+    rec[5] = ameta[i];
+    rec[6] = agid ? agid[i] : 0u;
+    rec[7] = 0u;
+    ameta[i] = PF_STATE_EMPTY;
+  }
 }
 
 // Placement order of arriving agents. After pf_agents_sort the arrays are [body (ordered by cell) |
@@ -527,59 +580,122 @@ __device__ __forceinline__ void mig_body_split(const uint32_t* body_chunks, long
   M = (T / 2) / kOwnChunk * kOwnChunk;
 }
 
+// free slots per chunk of 1024 candidate rank indices
 __global__ void __launch_bounds__(256)
-k_empty_flags(long long n, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ body_chunks,
-              unsigned long long* __restrict__ flags) {
-  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip >= n) return;
+k_empty_count(long long n, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ body_chunks,
+              uint32_t* __restrict__ emp_cnt) {
   long long T, M;
   mig_body_split(body_chunks, n, T, M);
-  const long long i = mig_slot_of_rank_index(ip, n, T, M);
-  flags[ip] = ((meta[i] & PF_META_STATE_MASK) == PF_STATE_EMPTY) ? 1ull : 0ull;
+  const long long ip0 = (long long)blockIdx.x * kOwnChunk + 4 * threadIdx.x;
+  unsigned cnt = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long ip = ip0 + q;
+    if (ip < n && (meta[mig_slot_of_rank_index(ip, n, T, M)] & PF_META_STATE_MASK) == PF_STATE_EMPTY) ++cnt;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  __shared__ unsigned part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned s = 0;
+    for (int w = 0; w < 8; ++w) s += part[w];
+    emp_cnt[blockIdx.x] = s;
+  }
 }
 
-__global__ void __launch_bounds__(256)
-k_migrate_fill(long long n, const unsigned long long* __restrict__ flags,
-               const unsigned long long* __restrict__ ranks, const uint32_t* __restrict__ buf,
-               const uint32_t* __restrict__ buf2, long long cap, float* ax, float* ay, float* ath,
-               float* awl, float* awr, uint32_t* ameta, uint32_t* agid,
-               unsigned long long* __restrict__ counters, const uint32_t* __restrict__ body_chunks) {
-  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip >= n) return;
-  long long T, M;
-  mig_body_split(body_chunks, n, T, M);
-  const long long i = mig_slot_of_rank_index(ip, n, T, M);  // slot this rank index stands for
-  // records of `buf` (from the strip above) take candidate ranks ascending, records of `buf2` (from
-  // the strip below) descending — see mig_slot_of_rank_index
-  unsigned long long m1 = buf ? buf[0] : 0ull;
-  if (m1 > (unsigned long long)cap) m1 = cap;
-  unsigned long long m2 = buf2 ? buf2[0] : 0ull;
-  if (m2 > (unsigned long long)cap) m2 = cap;
-  const unsigned long long m = m1 + m2;
-  if (ip == n - 1) {
-    unsigned long long empties = ranks[ip] + flags[ip];
-    unsigned long long placed = m < empties ? m : empties;
+// emp_base[c] = free slots before chunk c, emp_base[nc] = all of them; arrival counters
+__global__ void __launch_bounds__(1024)
+k_empty_offsets(int nc, long long cap, const uint32_t* __restrict__ emp_cnt, uint32_t* __restrict__ emp_base,
+                const uint32_t* __restrict__ buf, const uint32_t* __restrict__ buf2,
+                unsigned long long* __restrict__ counters) {
+  __shared__ typename cub::BlockScan<uint32_t, 1024>::TempStorage tmp;
+  __shared__ uint32_t carry;
+  const unsigned long long empties = mig_chunk_scan(emp_cnt, 1, 0, nc, emp_base, &carry, &tmp);
+  if (threadIdx.x == 0) {
+    emp_base[nc] = (uint32_t)empties;
+    unsigned long long m1 = buf ? buf[0] : 0ull, m2 = buf2 ? buf2[0] : 0ull;
+    if (m1 > (unsigned long long)cap) m1 = cap;
+    if (m2 > (unsigned long long)cap) m2 = cap;
+    const unsigned long long m = m1 + m2, placed = m < empties ? m : empties;
     atomicAdd(&counters[11], placed);
     if (m > placed) atomicAdd(&counters[12], m - placed);
   }
-  if (!flags[ip]) return;
-  const unsigned long long r = ranks[ip];
-  const unsigned long long empties = ranks[n - 1] + flags[n - 1];
-  const uint32_t* rec;
-  if (r < m1) {
-    rec = buf + (r + 1) * kMigWords;
+}
+
+// One warp per arriving record: records of `buf` (from the strip above) take the free slots in
+// candidate rank order ascending, records of `buf2` (from the strip below) descending. The warp finds
+// its rank's chunk by bisection of emp_base and the slot inside the chunk with 32 ballots at most.
+// Slots are only looked up here (slot_of[record] = slot or -1) and filled by k_migrate_fill, so that
+// every warp sees the same free slots the counts were taken from.
+__global__ void __launch_bounds__(256)
+k_migrate_find(long long n, int nc, const uint32_t* __restrict__ emp_base, const uint32_t* __restrict__ buf,
+               const uint32_t* __restrict__ buf2, long long cap, const uint32_t* __restrict__ ameta,
+               const uint32_t* __restrict__ body_chunks, long long* __restrict__ slot_of) {
+  const int lane = threadIdx.x & 31;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // record index over both buffers
+  unsigned long long m1 = buf ? buf[0] : 0ull, m2 = buf2 ? buf2[0] : 0ull;
+  if (m1 > (unsigned long long)cap) m1 = cap;
+  if (m2 > (unsigned long long)cap) m2 = cap;
+  if ((unsigned long long)w >= m1 + m2) return;
+  if (lane == 0) slot_of[w] = -1;
+  const unsigned long long empties = emp_base[nc];
+  unsigned long long r;  // candidate rank among the free slots
+  if ((unsigned long long)w < m1) {
+    r = (unsigned long long)w;
+    if (r >= empties) return;  // no room: dropped (counted in k_empty_offsets)
   } else {
-    const unsigned long long back = empties - 1 - r;  // 0 for the highest empty slot
-    if (back >= m2) return;  // stays empty (if slots run out, the ascending records keep theirs)
-    rec = buf2 + (back + 1) * kMigWords;
+    const unsigned long long back = (unsigned long long)w - m1;  // 0 takes the highest free slot
+    if (back >= empties || empties - 1 - back < m1) return;     // the ascending records keep theirs
+    r = empties - 1 - back;
   }
-  ax[i] = __uint_as_float(rec[0]);
-  ay[i] = __uint_as_float(rec[1]);
-  ath[i] = __uint_as_float(rec[2]);
-  awl[i] = __uint_as_float(rec[3]);
-  awr[i] = __uint_as_float(rec[4]);
-  ameta[i] = rec[5];
-  if (agid) agid[i] = rec[6];
+  int lo = 0, hi = nc;  // last chunk with emp_base[c] <= r
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((unsigned long long)emp_base[mid] <= r) lo = mid; else hi = mid;
+  }
+  long long T, M;
+  mig_body_split(body_chunks, n, T, M);
+  unsigned need = (unsigned)(r - emp_base[lo]);  // free slots of this chunk to skip
+  long long slot = -1;
+  for (int k = 0; k < kOwnChunk / 32; ++k) {
+    const long long ip = (long long)lo * kOwnChunk + 32 * k + lane;
+    const long long i = ip < n ? mig_slot_of_rank_index(ip, n, T, M) : -1;
+    const bool empty = i >= 0 && (ameta[i] & PF_META_STATE_MASK) == PF_STATE_EMPTY;
+    const unsigned m = __ballot_sync(0xffffffffu, empty);
+    const unsigned c = (unsigned)__popc(m);
+    if (need < c) {  // the need-th set bit of m
+      unsigned mm = m;
+      for (unsigned z = 0; z < need; ++z) mm &= mm - 1u;
+      const int src = __ffs(mm) - 1;
+      slot = __shfl_sync(0xffffffffu, i, src);
+      break;
+    }
+    need -= c;
+  }
+  if (lane == 0) slot_of[w] = slot;
+}
+
+// one thread per arriving record
+__global__ void __launch_bounds__(256)
+k_migrate_fill(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ buf2, long long cap,
+               const long long* __restrict__ slot_of, float* ax, float* ay, float* ath, float* awl, float* awr,
+               uint32_t* ameta, uint32_t* agid) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long m1 = buf ? buf[0] : 0ull, m2 = buf2 ? buf2[0] : 0ull;
+  if (m1 > (unsigned long long)cap) m1 = cap;
+  if (m2 > (unsigned long long)cap) m2 = cap;
+  if ((unsigned long long)w >= m1 + m2) return;
+  const long long slot = slot_of[w];
+  if (slot < 0) return;
+  const uint32_t* rec = (unsigned long long)w < m1 ? buf + (w + 1) * kMigWords : buf2 + (w - m1 + 1) * kMigWords;
+  ax[slot] = __uint_as_float(rec[0]);
+  ay[slot] = __uint_as_float(rec[1]);
+  ath[slot] = __uint_as_float(rec[2]);
+  awl[slot] = __uint_as_float(rec[3]);
+  awr[slot] = __uint_as_float(rec[4]);
+  ameta[slot] = rec[5];
+  if (agid) agid[slot] = rec[6];
 }
 
 // ------------------------------------------------------------------------------------------

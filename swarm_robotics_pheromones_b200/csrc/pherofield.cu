@@ -81,8 +81,11 @@ struct pf_handle {
   struct PeerLink { float* buf[2]; unsigned int* flags; long long rows, pitch, chan_stride; int set; } peer_up, peer_dn;
   unsigned int* peer_flags;  // device: [0] written by the strip above, [1] by the strip below
   unsigned int peer_epoch;
-  long long mig_flags_n;   // > 0: scratch holds the migration flags the last move kernel wrote
+  long long mig_flags_n;   // > 0: mig_cnt holds the per-chunk leaver counts the last move kernel made
   const float* mig_flags_x;
+  uint32_t *mig_cnt, *mig_base, *emp_cnt, *emp_base;  // per chunk (two-level migration, pf_agents.cuh)
+  long long* mig_slot_of;
+  long long mig_slot_cap;
   TmaStencilState tma;
   // profiling: ring of per-tick events
   int prof_on;
@@ -354,6 +357,11 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->own_smin) cudaFree(h->own_smin);
   if (h->own_body) cudaFree(h->own_body);
   if (h->own_tail) cudaFree(h->own_tail);
+  if (h->mig_cnt) cudaFree(h->mig_cnt);
+  if (h->mig_base) cudaFree(h->mig_base);
+  if (h->emp_cnt) cudaFree(h->emp_cnt);
+  if (h->emp_base) cudaFree(h->emp_base);
+  if (h->mig_slot_of) cudaFree(h->mig_slot_of);
   tile_free(h);
   if (h->counters) cudaFree(h->counters);
   if (h->d_sum) cudaFree(h->d_sum);
@@ -404,6 +412,12 @@ extern "C" int pf_reserve_agents(pf_handle* h, int64_t max_agents) {
     h->own_alloc = cap / kOwnChunk + 2;
     for (auto pp : arrs) PF_CUDA(h, cudaMalloc(pp, sizeof(uint32_t) * h->own_alloc));
     h->own_n = 0;
+    uint32_t** migs[4] = {&h->mig_cnt, &h->mig_base, &h->emp_cnt, &h->emp_base};
+    for (auto pp : migs) {
+      if (*pp) cudaFree(*pp);
+      *pp = nullptr;
+      PF_CUDA(h, cudaMalloc(pp, sizeof(uint32_t) * 2 * h->own_alloc));
+    }
   }
   return PF_OK;
 }
@@ -850,10 +864,12 @@ extern "C" int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y,
 
 static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s,
                               bool emit_next_keys = false, const TileBins* bins = nullptr) {
-  // on a strip, the move kernel also emits the leave-up / leave-down flags pf_migrate_pack needs
-  unsigned long long* mig = nullptr;
-  if (is_sharded(h) && (flags & PF_STEP_MOVE) && h->scratch && a->n <= h->cap) {
-    mig = (unsigned long long*)h->scratch;
+  // on a strip, the move kernel also counts the leavers per chunk for pf_migrate_pack
+  uint32_t* mig = nullptr;
+  if (is_sharded(h) && (flags & PF_STEP_MOVE) && h->mig_cnt && a->n <= h->cap) {
+    mig = h->mig_cnt;
+    const long long nc = (a->n + kOwnChunk - 1) / kOwnChunk;
+    PF_CUDA(h, cudaMemsetAsync(mig, 0, sizeof(uint32_t) * 2 * nc, s));
     h->mig_flags_n = a->n;
     h->mig_flags_x = a->x;
   }
@@ -861,7 +877,7 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
   float* nv = nullptr;
   TileBins no_bins;
   memset(&no_bins, 0, sizeof(no_bins));
-  if (emit_next_keys && !mig) {  // keys_in / vals_in of the sort scratch, for the next tick's deposit
+  if (emit_next_keys) {  // keys_in / vals_in of the sort scratch, for the next tick's deposit
     nk = (uint32_t*)h->scratch;
     nv = (float*)(nk + 2 * h->cap);
   }
@@ -1243,18 +1259,17 @@ extern "C" int pf_migrate_pack(pf_handle* h, const pf_agents* a, uint32_t* up_bu
   }
   rc = pf_reserve_agents(h, a->n);
   if (rc) return rc;
-  unsigned long long* flags = (unsigned long long*)h->scratch;
-  unsigned long long* ranks = flags + h->cap;
-  if (h->mig_flags_n != a->n || h->mig_flags_x != a->x) {
-    k_migrate_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, flags);
+  const int nc = (int)((a->n + kOwnChunk - 1) / kOwnChunk);
+  if (h->mig_flags_n != a->n || h->mig_flags_x != a->x) {  // the agents were moved by somebody else: count now
+    PF_CUDA(h, cudaMemsetAsync(h->mig_cnt, 0, sizeof(uint32_t) * 2 * nc, s));
+    k_migrate_count<<<blocks_for(a->n, 256), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, h->mig_cnt);
     PF_LAUNCH_CHECK(h);
   }
   h->mig_flags_n = 0;
-  size_t bytes = h->cub_temp_bytes;
-  PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
-  k_migrate_scatter<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, cap, flags, ranks, a->x, a->y, a->theta,
-                                                         a->wl, a->wr, a->meta, a->gid, up_buf, down_buf,
-                                                         h->counters);
+  k_migrate_offsets<<<1, 1024, 0, s>>>(nc, cap, h->mig_cnt, h->mig_base, up_buf, down_buf, h->counters);
+  PF_LAUNCH_CHECK(h);
+  k_migrate_scatter<<<nc, 256, 0, s>>>(h->dev, a->n, cap, h->mig_cnt, h->mig_base, a->x, a->y, a->theta, a->wl,
+                                       a->wr, a->meta, a->gid, up_buf, down_buf);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -1275,16 +1290,25 @@ extern "C" int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32
   if (rc) return rc;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned long long* flags = (unsigned long long*)h->scratch;
-  unsigned long long* ranks = flags + h->cap;
   // the body/tail split of the last pf_agents_sort of these arrays steers where arrivals are put
   const uint32_t* body = (h->own_n == a->n && h->own_x == a->x) ? h->own_body : nullptr;
-  k_empty_flags<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, a->meta, body, flags);
+  const int nc = (int)((a->n + kOwnChunk - 1) / kOwnChunk);
+  if (h->mig_slot_cap < 2 * cap) {
+    if (h->mig_slot_of) cudaFree(h->mig_slot_of);
+    h->mig_slot_of = nullptr;
+    PF_CUDA(h, cudaMalloc(&h->mig_slot_of, sizeof(long long) * (size_t)(2 * cap > 0 ? 2 * cap : 1)));
+    h->mig_slot_cap = 2 * cap;
+  }
+  k_empty_count<<<nc, 256, 0, s>>>(a->n, a->meta, body, h->emp_cnt);
   PF_LAUNCH_CHECK(h);
-  size_t bytes = h->cub_temp_bytes;
-  PF_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_temp, bytes, flags, ranks, (int)a->n, s));
-  k_migrate_fill<<<blocks_for(a->n, 256), 256, 0, s>>>(a->n, flags, ranks, buf, buf2, cap, a->x, a->y, a->theta,
-                                                      a->wl, a->wr, a->meta, a->gid, h->counters, body);
+  k_empty_offsets<<<1, 1024, 0, s>>>(nc, cap, h->emp_cnt, h->emp_base, buf, buf2, h->counters);
+  PF_LAUNCH_CHECK(h);
+  // one warp per record that may arrive (the headers stay on the device: the grid covers 2 * cap)
+  k_migrate_find<<<blocks_for(2 * cap * 32, 256), 256, 0, s>>>(a->n, nc, h->emp_base, buf, buf2, cap, a->meta, body,
+                                                               h->mig_slot_of);
+  PF_LAUNCH_CHECK(h);
+  k_migrate_fill<<<blocks_for(2 * cap, 256), 256, 0, s>>>(buf, buf2, cap, h->mig_slot_of, a->x, a->y, a->theta,
+                                                          a->wl, a->wr, a->meta, a->gid);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
