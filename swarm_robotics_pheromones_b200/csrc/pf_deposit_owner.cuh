@@ -367,8 +367,12 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
                 const uint32_t* __restrict__ keys, const float* __restrict__ vals, uint32_t sentinel,
                 const uint32_t* __restrict__ split, const uint32_t* __restrict__ pmax,
                 const uint32_t* __restrict__ smin, const uint32_t* __restrict__ tail_list,
-                float* __restrict__ field, PeerRows peer, const uint32_t* __restrict__ only_if) {
+                float* __restrict__ field, PeerRows peer, const uint32_t* __restrict__ only_if,
+                uint32_t handed_lo, uint32_t handed_hi, const uint32_t* __restrict__ handed_flag) {
   if (only_if && *only_if == 0u) return;  // the stencil already applied this tick's deposits (pf_deposit_tile.cuh)
+  // strips: the cells [handed_lo, handed_hi) of every channel got their deposits from the stencil
+  // (unless its flag says otherwise); key ranges inside them have nothing to do
+  const bool handed = handed_flag && *handed_flag == 0u;
   typedef cub::BlockScan<int, kOwnThreads> Scan;
   __shared__ typename Scan::TempStorage scan_tmp;
   __shared__ OwnScratch u;
@@ -394,6 +398,7 @@ k_deposit_owner(PFDev p, long long n, int all_chunks, const uint32_t* __restrict
     st_lo[0] = split[b];
     st_hi[0] = split[b + 1];
     st_n = (split[b] < split[b + 1]) ? 1 : 0;
+    if (handed && split[b] >= handed_lo && split[b + 1] <= handed_hi) st_n = 0;
   }
   __syncthreads();
 

@@ -68,6 +68,7 @@ struct pf_handle {
   int no_tile_deposit;
   bool tile_pending;      // lists are ready for (pf_step: were given to) the stencil launch over tile_ty0..ty1
   bool tile_handed;       // strips: that launch has happened; the next pf_agents_deposit skips those agents
+  uint32_t own_handed_lo, own_handed_hi;  // ... and the sort-free deposit kernel skips key ranges inside these cells
   int tile_ty0, tile_ty1; // tile rows handed over
   unsigned long long tile_attempts, g_tile_attempts;
   long long own_alloc;      // chunks allocated
@@ -773,7 +774,9 @@ static int owner_sum(pf_handle* h, long long n, cudaStream_t s, uint32_t* only_i
   const int grid = only_if ? (nchunks < 4 * h->n_sm ? nchunks : 4 * h->n_sm) : nchunks;
   k_deposit_owner<<<grid, kOwnThreads, 0, s>>>(h->dev, n, nchunks, h->own_body, keys_in, vals_in, h->sentinel,
                                                h->own_split, h->own_pmax, h->own_smin, h->own_tail,
-                                               h->buf[h->cur], peer_rows(h, h->cur), only_if);
+                                               h->buf[h->cur], peer_rows(h, h->cur), only_if, h->own_handed_lo,
+                                               h->own_handed_hi, h->own_handed_hi ? h->tile_flag : nullptr);
+  h->own_handed_lo = h->own_handed_hi = 0;
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -831,6 +834,7 @@ extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream)
   const bool own = owner_ready(h, a);
   TileBins handed;
   memset(&handed, 0, sizeof(handed));
+  h->own_handed_lo = h->own_handed_hi = 0;
   if (h->tile_handed) {  // the last stencil took the interior tile rows' deposits (unless its flag says otherwise)
     handed.bcnt = h->tile_bcnt;
     handed.nx = (h->dev.W + kTileCols - 1) / kTileCols;
@@ -838,6 +842,9 @@ extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream)
     handed.ty_lo = h->tile_ty0;
     handed.ty_hi = h->tile_ty1;
     h->tile_handed = false;
+    const long long r1 = (long long)h->tile_ty1 * kTileRows < h->dev.rows ? (long long)h->tile_ty1 * kTileRows : h->dev.rows;
+    h->own_handed_lo = (uint32_t)((long long)h->tile_ty0 * kTileRows * h->dev.W);
+    h->own_handed_hi = (uint32_t)(r1 * h->dev.W);
   }
   k_deposit_keys_agents<<<wave_grid(a->n, h->wave_keys), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, keys_in,
                                                              vals_in, h->sentinel, h->counters,

@@ -244,9 +244,9 @@ class StripWorker:
         if self.dep[1] > self.dep[0]:
             d0, d1 = self.dep
             self.b.field_rows(d0, d1)          # ONE call over exactly these rows: the deposits ride along
-            last_done = d1 >= rows              # arena edge below: the range runs to the last row
-            if hi > d1:
-                self.b.field_rows(d1, hi)
+            last_done = True
+            if d1 < rows:                       # the band below it, last row included (one launch)
+                self.b.field_rows(d1, rows)
         elif hi > mid:
             self.b.field_rows(mid, hi)
         self.b.field_rows(0, min(1, rows))
