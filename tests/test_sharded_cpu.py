@@ -136,3 +136,53 @@ def test_gloo_world2_equals_unsharded(tmp_path):
     got = gather_agents_sorted([{f: r[f] for f in dense.AgentsNP.FIELDS} for r in ranks])
     for f in dense.AgentsNP.FIELDS:
         assert (got[f].view(np.uint32) == getattr(a, f).view(np.uint32)).all(), f
+
+
+def test_worker_row_schedule_covers_every_row_exactly_once():
+    # the stencil launches of one tick, with and without a hand-over range: every local row exactly once,
+    # the hand-over rows as ONE call after the move kernel, nothing but rows [1, r0) before it
+    class Rec:
+        def __init__(self, rows, dep):
+            self.rows, self._dep, self.calls, self.flags = rows, dep, [], None
+        def tile_rows(self):
+            return self._dep
+        def field_rows(self, r0, r1):
+            self.calls.append(("rows", r0, r1))
+        def agents(self, flags):
+            self.flags = flags
+            self.calls.append(("agents",))
+        def swap(self):
+            self.calls.append(("swap",))
+
+    for rows, dep in [(384, (64, 320)), (384, (64, 384)), (256, (0, 0)), (4096, (512, 4032)), (1, (0, 0)), (2, (0, 0))]:
+        b = Rec(rows, dep)
+        w = sharded.StripWorker(b, 1, 3)
+        w.begin_tick(True)
+        w.field_interior_a()
+        w.agents(True)
+        w.field_rest()
+        seen = np.zeros(rows, dtype=int)
+        before_agents = True
+        for c in b.calls:
+            if c[0] == "agents":
+                before_agents = False
+            elif c[0] == "rows":
+                seen[c[1]:c[2]] += 1
+                if before_agents:
+                    assert c[1] == 1 and (dep[1] <= dep[0] or c[2] == dep[0])
+        assert (seen == 1).all(), (rows, dep, b.calls)
+        if dep[1] > dep[0]:
+            assert ("rows", dep[0], dep[1]) in b.calls and b.flags & abi.STEP_HANDOVER
+        else:
+            assert not (b.flags & abi.STEP_HANDOVER)
+        assert b.calls[-1] == ("swap",)
+        # no hand-over asked for: the old half / half split
+        b2 = Rec(rows, dep)
+        w2 = sharded.StripWorker(b2, 1, 3)
+        w2.begin_tick(False)
+        w2.field_interior_a(); w2.agents(True); w2.field_rest()
+        seen = np.zeros(rows, dtype=int)
+        for c in b2.calls:
+            if c[0] == "rows":
+                seen[c[1]:c[2]] += 1
+        assert (seen == 1).all() and not (b2.flags & abi.STEP_HANDOVER)
