@@ -16,12 +16,13 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
                       const float* __restrict__ y, uint32_t* __restrict__ meta,
                       uint32_t* __restrict__ keys, float* __restrict__ vals, uint32_t sentinel,
                       unsigned long long* __restrict__ counters, uint32_t* __restrict__ cmin,
-                      uint32_t* __restrict__ cmax, TileBins handed, const uint32_t* __restrict__ handed_flag) {
+                      uint32_t* __restrict__ cmax, TileBins handed, uint32_t* __restrict__ handed_flag) {
   // handed.bcnt != null: the last move kernel handed the deposits of the tile rows [ty_lo, ty_hi)
   // to the stencil (counter already bumped). *handed_flag == 0: the stencil applied them, nothing
   // left to do for those agents; != 0: it could not (a crowded tile) and they are deposited here
   // after all, with the amount their bumped counter says.
   const bool handed_done = handed.bcnt && *handed_flag == 0u;
+  if (handed.bcnt && !handed_done && blockIdx.x == 0 && threadIdx.x == 0) handed_flag[1] += 1u;  // pf_tile_stats
   // grid-stride over a fixed grid (a multiple of the SM count): the deposit counter costs one
   // global atomic per CTA instead of one per warp (same-address atomics serialise in L2)
   __shared__ unsigned int s_dep;

@@ -94,3 +94,42 @@ def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
         attempted, fell_back = w.b.field.tile_stats()
         assert attempted == nticks - 3 and fell_back == 0, (w.rank, attempted, fell_back)
         w.b.field.close()
+
+
+def test_strip_hand_over_falls_back_when_an_interior_tile_is_crowded():
+    # 5000 robots inside one interior tile of strip 0: its bin overflows, the flag is raised on the device,
+    # the stencil leaves its output alone and the NEXT tick's key kernel deposits the handed robots after
+    # all (with the amount their already bumped counter says) — same bits as the oracle
+    cfg, x, y, th, st = _scenario(seed=23, n=14000, H=768, W=512, C=2)
+    rng = np.random.default_rng(5)
+    x[:5000] = (0.70 + rng.uniform(0, 0.50, 5000)).astype(np.float32)   # rows 70..120 of strip 0: inside tile row 1
+    y[:5000] = (1.00 + rng.uniform(0, 2.00, 5000)).astype(np.float32)
+    nticks, world = 12, 2
+    o = dense.DenseOracle(cfg)
+    a = dense.AgentsNP(x, y, th, st)
+    o.tick(a, nticks)
+    parts = sharded.partition_agents(cfg, world, x, y, th, st)
+    workers = []
+    for r in range(world):
+        p = parts[r]
+        strip = sharded.CudaStrip(sharded.strip_config(cfg, world, r), p["x"], p["y"], p["theta"],
+                                  p["state"], p["gid"], capacity=16000, migrate_cap=1024)
+        strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
+        workers.append(sharded.StripWorker(strip, r, world))
+    drv = sharded.LocalDriver(workers)
+    for w in workers:
+        w.b.sort_agents()
+    for t in range(nticks):
+        drv.tick(True, hand_over=t != nticks - 1)
+    torch.cuda.synchronize()
+    field = np.concatenate([w.b.field.snapshot() for w in workers], axis=1)
+    assert (field.view(np.uint32) == np.ascontiguousarray(o.field).view(np.uint32)).all()
+    got = gather_agents_sorted([w.b.swarm.to_numpy() for w in workers])
+    for f in dense.AgentsNP.FIELDS:
+        assert (got[f].view(np.uint32) == getattr(a, f).view(np.uint32)).all(), f
+    assert sum(w.b.field.counters().deposits for w in workers) == int(o.counters[8])
+    s0, s1 = workers[0].b.field.tile_stats(), workers[1].b.field.tile_stats()
+    assert s0 == (nticks - 1, nticks - 1), s0     # crowded strip: every hand-over fell back
+    assert s1 == (nticks - 1, 0), s1              # its neighbour: none did
+    for w in workers:
+        w.b.field.close()
