@@ -10,8 +10,17 @@ W8 = abi.PF_MIGRATE_WORDS
 
 
 class OracleStrip:
-    def __init__(self, cfg, x, y, theta, state, gid, capacity, migrate_cap):
+    """hand_over=True also emulates the library's PF_STEP_HANDOVER protocol (pf_tile_rows): the robots that
+    end up in the interior rows have their NEXT deposit added to those rows of the next buffer by the
+    stencil call over exactly that range, and are skipped by the next deposit() — so that the driver's
+    ordering of the phases can be checked on CPU."""
+
+    def __init__(self, cfg, x, y, theta, state, gid, capacity, migrate_cap, hand_over=False):
         self.cfg = cfg
+        self.hand_over = hand_over
+        self._delta = None      # (r0, r1, [C][r1-r0][W] sums) waiting for the stencil call over (r0, r1)
+        self._handed = None     # (r0, r1) whose robots the next deposit() skips
+        self.handed_ticks = 0
         self.o = dense.DenseOracle(cfg)
         self.rows = cfg.row1 - cfg.row0
         n = len(x)
@@ -39,8 +48,37 @@ class OracleStrip:
     def ghost_rows(self):
         return self._rows(0), self._rows(self.rows + 1)
 
+    def tile_rows(self):
+        """the library's rule in small: whole 64-row bands, not the first one, not the last 64+ rows next to a
+        neighbour"""
+        if not self.hand_over:
+            return (0, 0)
+        lo = 64
+        hi = ((self.rows - 64) // 64) * 64 if self.cfg.row1 < self.cfg.H else self.rows
+        return (lo, hi) if hi > lo else (0, 0)
+
+    def _depositors_in(self, r0, r1):
+        a = self.a
+        r, _, inside = dense.cells_of(self.cfg, a.x, a.y)
+        st = a.meta & 3
+        moved = (a.meta & abi.META_MOVED) != 0
+        lr = r - self.cfg.row0
+        return ((st == abi.STATE_SEARCHING) | (st == abi.STATE_HOMING)) & moved & inside & (lr >= r0) & (lr < r1)
+
+    def _deposit_subset(self, oracle, idx):
+        sub = self.a.select(idx)
+        m = oracle.agents_deposit(sub)
+        self.a.meta[idx] = sub.meta
+        return m
+
     def deposit(self):
-        self.o.agents_deposit(self.a)
+        if self._handed is None:
+            self.o.agents_deposit(self.a)
+            return
+        r0, r1 = self._handed
+        self._handed = None
+        rest = np.nonzero(~self._depositors_in(r0, r1))[0]   # array order is kept
+        self._deposit_subset(self.o, rest)
 
     def field_rows(self, r0, r1):
         # the oracle steps whole strips: do it once, on the first call of the tick
@@ -50,11 +88,28 @@ class OracleStrip:
             dense.lib().po_step_field(C.byref(self.o.cfg), dense._fp(self.o.bufs[self.o.cur]),
                                       dense._fp(self.o.bufs[self.o.cur ^ 1]))
             self._stepped = True
+        if self._delta is not None and (r0, r1) == self._delta[:2]:
+            nxt = self.o._view(self.o.cur ^ 1)[:, 1:-1, :]
+            nxt[:, r0:r1, :] += self._delta[2]            # next[cell] = stencil value + ordered sum
+            self._handed = (r0, r1)
+            self._delta = None
+            self.handed_ticks += 1
 
     def agents(self, flags):
-        self.o.agents_step(self.a, flags)
+        self.o.agents_step(self.a, flags & ~abi.STEP_HANDOVER)
+        if flags & abi.STEP_HANDOVER:
+            r0, r1 = self.tile_rows()
+            assert r1 > r0, "hand-over asked for without a row range"
+            idx = np.nonzero(self._depositors_in(r0, r1))[0]
+            if not hasattr(self, "_o2"):
+                self._o2 = dense.DenseOracle(self.cfg)
+            self._o2.field[...] = 0
+            m = self._deposit_subset(self._o2, idx)       # bumps their counters now, as the move kernel does
+            self.o.counters[8] += np.uint64(m)
+            self._delta = (r0, r1, self._o2.field[:, r0:r1, :].copy())
 
     def swap(self):
+        assert self._delta is None, "handed-over rows were not stepped as one call"
         self.o.cur ^= 1
         self._stepped = False
 

@@ -186,3 +186,67 @@ def test_worker_row_schedule_covers_every_row_exactly_once():
             if c[0] == "rows":
                 seen[c[1]:c[2]] += 1
         assert (seen == 1).all() and not (b2.flags & abi.STEP_HANDOVER)
+
+
+def _make_ho_worker(cfg, world, rank, parts):
+    scfg = sharded.strip_config(cfg, world, rank)
+    p = parts[rank]
+    b = OracleStrip(scfg, p["x"], p["y"], p["theta"], p["state"], p["gid"], len(p["x"]) * 2 + 64, 512,
+                    hand_over=True)
+    return sharded.StripWorker(b, rank, world)
+
+
+def _ho_scenario():
+    return _scenario(seed=9, n=2500, H=640, W=64, C=2)   # strips of 320 / 213 rows: interior 64-row bands exist
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_local_driver_with_hand_over_equals_unsharded(world):
+    # the hand-over protocol (pf_tile_rows / PF_STEP_HANDOVER) driven by the same worker code as on the GPU,
+    # with the oracle backend emulating what the library does
+    cfg, x, y, th, st = _ho_scenario()
+    nticks = 60
+    o, a = _reference_run(cfg, x, y, th, st, nticks)
+    parts = sharded.partition_agents(cfg, world, x, y, th, st)
+    workers = [_make_ho_worker(cfg, world, r, parts) for r in range(world)]
+    drv = sharded.LocalDriver(workers)
+    for t in range(nticks):
+        drv.tick(True, hand_over=t != nticks - 1 and t % 7 != 3)   # some ticks without, never the last one
+    field = np.concatenate([w.b.o.field for w in workers], axis=1)
+    assert (field.view(np.uint32) == np.ascontiguousarray(o.field).view(np.uint32)).all()
+    got = gather_agents_sorted([{f: getattr(w.b.a, f) for f in dense.AgentsNP.FIELDS} for w in workers])
+    for f in dense.AgentsNP.FIELDS:
+        assert (got[f].view(np.uint32) == getattr(a, f).view(np.uint32)).all(), f
+    assert all(w.b.handed_ticks == sum(1 for t in range(nticks) if t != nticks - 1 and t % 7 != 3) for w in workers)
+    assert sum(int(w.b.o.counters[8]) for w in workers) == int(o.counters[8])
+
+
+def _gloo_rank_ho(rank, world, port, nticks, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg, x, y, th, st = _ho_scenario()
+    parts = sharded.partition_agents(cfg, world, x, y, th, st)
+    w = _make_ho_worker(cfg, world, rank, parts)
+    drv = sharded.DistDriver(w)
+    for t in range(nticks):
+        drv.tick(True, hand_over=t != nticks - 1)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), field=w.b.o.field, handed=w.b.handed_ticks,
+             **{f: getattr(w.b.a, f) for f in dense.AgentsNP.FIELDS})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_with_hand_over_equals_unsharded(tmp_path):
+    world, nticks = 2, 40
+    cfg, x, y, th, st = _ho_scenario()
+    o, a = _reference_run(cfg, x, y, th, st, nticks)
+    mp.spawn(_gloo_rank_ho, args=(world, _free_port(), nticks, str(tmp_path)), nprocs=world, join=True)
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    field = np.concatenate([r["field"] for r in ranks], axis=1)
+    assert (field.view(np.uint32) == np.ascontiguousarray(o.field).view(np.uint32)).all()
+    got = gather_agents_sorted([{f: r[f] for f in dense.AgentsNP.FIELDS} for r in ranks])
+    for f in dense.AgentsNP.FIELDS:
+        assert (got[f].view(np.uint32) == getattr(a, f).view(np.uint32)).all(), f
+    assert all(int(r["handed"]) == nticks - 1 for r in ranks)
