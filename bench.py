@@ -478,9 +478,14 @@ def run_sharded(args):
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    # keep stdout to the one JSON line: NCCL's banner / warnings go to a file
-    os.environ["NCCL_DEBUG"] = os.environ.get("PF_NCCL_DEBUG", "WARN")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pf_nccl_%h_%p.log")
+    # stdout carries the one JSON line, so NCCL's log (INFO unless the caller chose a level) goes to a per-rank
+    # file and its communicator lines (nranks, transport, NVLS) are copied to STDERR at the end of the run
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+    nccl_log = None
+    if "NCCL_DEBUG_FILE" not in os.environ:
+        nccl_log = f"/tmp/pf_nccl_{os.getpid()}.log"
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
     scfg = sharded.strip_config(cfg, world, rank, device=local)
@@ -496,7 +501,8 @@ def run_sharded(args):
     del x, y, th, rows
     strip.field.set_stencil_variant(args.variant, args.rows_per_cta)
     worker = sharded.StripWorker(strip, rank, world)
-    drv = sharded.DistDriver(worker, overlap=not args.no_overlap, profile=args.phase_profile)
+    drv = sharded.DistDriver(worker, overlap=not args.no_overlap, profile=args.phase_profile,
+                             legacy=args.legacy_loop or args.nccl_halo)
     if not args.nccl_halo:
         # halo exchange fused into the deposit / stencil kernels: edge rows are stored straight into
         # the neighbours' ghost rows over NVLink (CUDA IPC mappings); NCCL only carries migrants
@@ -538,6 +544,12 @@ def run_sharded(args):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = strip.field.launch_count() - l0
+    strip.field.peer_status()  # raises if a bounded peer wait gave up (a rank out of lockstep)
+    c_run = strip.field.counters()
+    lost = torch.tensor([float(c_run.migrate_dropped), float(c_run.migrated_out), float(c_run.migrated_in)],
+                        device="cuda", dtype=torch.float64)
+    dist.all_reduce(lost)
+    assert lost[0].item() == 0, f"{int(lost[0].item())} migrating agents were dropped (migration mailbox too small)"
 
     # stencil-only time of this strip (roofline per GPU), same event method
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -621,6 +633,10 @@ def run_sharded(args):
                          "algorithmic_bytes_per_launch": local_cells * BYTES_PER_CELL_UPDATE},
             "cpu_baseline": None,
             "agents_per_rank": [int(c.item()) for c in allc],
+            "agent_imbalance_max_over_mean": float(max(c.item() for c in allc) / max(1.0, np.mean([c.item() for c in allc]))),
+            "migrated_agents_total": int(lost[1].item()), "migrate_dropped": int(lost[0].item()),
+            "tick_driver": ("host loop, NCCL migration (round-1 path)" if (args.legacy_loop or args.nccl_halo or args.phase_profile)
+                            else "pf_strip_tick: one C call per tick, leavers through peer mailboxes"),
             "halo_overlap": not args.no_overlap, "stencil_variant": args.variant,
             "halo": "nccl send/recv" if args.nccl_halo else "peer stores fused into the kernels (CUDA IPC, NVLink P2P)",
             "agent_sort_every": args.sort_every,
@@ -632,6 +648,17 @@ def run_sharded(args):
     dist.barrier()
     strip.field.close()
     dist.destroy_process_group()
+    if nccl_log and os.path.exists(nccl_log):  # the communicator lines, for whoever checks the rank count
+        keep = ("nranks", "Init COMPLETE", "NVLS", "comm 0x", "NCCL version", "Connected", "P2P")
+        try:
+            with open(nccl_log) as fh:
+                lines = [ln.rstrip() for ln in fh if any(k in ln for k in keep)]
+            for ln in lines[:40] if rank == 0 else lines[:4]:
+                print(ln, file=sys.stderr)
+            sys.stderr.flush()
+            os.unlink(nccl_log)
+        except OSError:
+            pass
 
 
 def main():
@@ -657,6 +684,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="sharded run: NCCL send/recv halo instead of peer stores")
     ap.add_argument("--phase-profile", action="store_true", help="sharded run: per-phase CUDA events")
+    ap.add_argument("--legacy-loop", action="store_true",
+                    help="sharded run: round-1 tick driver (phase-by-phase host loop, NCCL migration)")
     ap.add_argument("--no-hand-over", action="store_true",
                     help="sharded run: always use the separate deposit kernel (no deposits riding on the stencil)")
     args = ap.parse_args()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 
 #define PF_MAX_CHANNELS 4
 #define PF_MAX_FOOD 16
@@ -75,7 +75,11 @@ extern "C" {
 #define PF_META_DEC_MASK 0x38u
 #define PF_META_CARRY 0x40u            /* bit 6: carrying food (fsm mode)                       */
 #define PF_META_HASPOS 0x80u           /* bit 7: a previous observed position exists (sup:281)  */
-#define PF_META_COUNT_SHIFT 8          /* bits 8-31: deposits made so far (len(global grid))    */
+#define PF_META_COUNT_SHIFT 8          /* bits 8-30: deposits made so far (len(global grid))    */
+#define PF_META_COUNT_MASK 0x7FFFFFu   /* 23 bits                                               */
+#define PF_META_HANDED 0x80000000u     /* bit 31: this robot's NEXT deposit was handed to the stencil of the
+                                          tick that just ran (strips, PF_STEP_HANDOVER); set by the move
+                                          kernel, cleared by the next deposit. Never set between pf_step calls */
 
 /* step flags */
 #define PF_STEP_DEPOSIT 0x1u /* run deposit_pheromone                                   sup:577 */
@@ -138,6 +142,9 @@ typedef struct pf_config {
   float dt;                 /* 0.064 s: two 32 ms Webots steps per controller tick */
   float wheel_radius;       /* 0.02 m,  E-puck.proto:100 */
   float axle_length;        /* 0.052 m, E-puck.proto:86  */
+
+  /* ---- multi-GPU strips: records per direction per tick the migration mailbox can take; 0 = default (16384) */
+  int32_t migrate_cap;
 } pf_config;
 
 /* Agents, structure-of-arrays, caller-owned device memory. `n` slots are processed; slots whose
@@ -162,6 +169,7 @@ typedef struct pf_counters {
   uint64_t migrated_out;    /* agents packed for a neighbour strip */
   uint64_t migrated_in;
   uint64_t migrate_dropped; /* records that did not fit a send buffer or found no empty slot */
+  uint64_t peer_timeouts;   /* pf_peer_wait / migration waits that gave up (neighbour strip dead or out of lockstep) */
 } pf_counters;
 
 typedef struct pf_handle pf_handle;
@@ -304,8 +312,11 @@ int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32_t* buf, co
 typedef struct pf_peer_info {
   void* buf0;  /* the strip's mailboxes for buffer parity 0 / 1 (device pointers valid in THIS process) */
   void* buf1;
-  void* flags; /* two u32 epoch words: [0] written by the strip above, [1] by the strip below */
+  void* flags; /* u32 epoch words: halo [0] written by the strip above, [1] by the strip below; migration [2], [3] */
   int64_t rows, pitch, chan_stride;
+  void* mig;   /* migration mailbox: two record buffers of (mig_cap + 1) * PF_MIGRATE_WORDS u32 — [0] filled by the
+                  strip above, [1] by the strip below (pf_strip_tick packs leavers straight into the neighbour's) */
+  int64_t mig_cap;
 } pf_peer_info;
 int pf_peer_export(pf_handle* h, pf_peer_info* out);                /* this strip, raw pointers */
 int pf_peer_ipc_handles(pf_handle* h, uint8_t* out192);             /* cudaIpcMemHandle_t + pad  */
@@ -315,6 +326,32 @@ int pf_peer_push_edges(pf_handle* h, void* stream);
 int pf_peer_signal(pf_handle* h, void* stream);
 int pf_peer_wait(pf_handle* h, void* stream);
 
+/* PF_ESTATE when a bounded peer wait gave up since the last pf_counters_reset (a neighbour strip is dead or the
+ * strips do not tick in lockstep): the stream is not wedged, but field and agents are no longer valid.
+ * Synchronises the stream. */
+int pf_peer_status(pf_handle* h, void* stream);
+
+/* One whole tick of a row strip enqueued by ONE call — no host round trips between the phases, leavers packed
+ * straight into the neighbours' migration mailboxes over NVLink (peer stores + an epoch flag, like the halo; no
+ * NCCL message). Needs pf_peer_attach on the sides that have a neighbour (pf_peer_info.mig set). `flags`:
+ * PF_STEP_DEPOSIT (deposit_pheromone), PF_STEP_SENSE, PF_STEP_MOVE (without it nothing migrates), and
+ * PF_STEP_HANDOVER = the interior rows' next deposits may ride on this tick's stencil (see pf_tile_rows: not on
+ * the last tick before the field is read nor on the tick before pf_agents_sort). The field step always runs.
+ * `phases`: PF_TICK_ALL for one process per GPU. Several strips driven by ONE host thread on ONE stream (tests)
+ * must interleave: phase A for every strip, then B for every strip, then C — a strip's wait can only be
+ * satisfied by kernels enqueued before it.
+ *   A: deposit -> halo signal
+ *   B: stencil over the first rows -> halo wait -> sense/decide/move (+ hand-over) -> pack leavers -> migration signal
+ *   C: stencil over the remaining rows (handed deposits ride along) -> swap -> migration wait -> unpack
+ * Replaces Controller.startPheromone / homing (sup:565-607, 627-663) on a strip; order as pf_step. */
+#define PF_TICK_A 0x1u
+#define PF_TICK_B 0x2u
+#define PF_TICK_C 0x4u
+#define PF_TICK_ALL 0x7u
+int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, uint32_t phases, void* stream);
+
+/* pf_snapshot_host, pf_field_sum_host and pf_counters_host return PF_ESTATE between a hand-over tick and the next
+ * deposit (the interior rows and the deposit counters are one tick ahead). */
 int pf_counters_host(pf_handle* h, pf_counters* out_host, void* stream);
 int pf_counters_reset(pf_handle* h, void* stream);
 
@@ -411,6 +448,7 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
 #define PF_OPT_NO_TILE_DEPOSIT 6 /* pf_step: never hand the next tick's deposits to the stencil kernel
                                    (default: done where the sort-free deposit is in use and the TMA
                                    stencil runs; falls back on the device when a tile is too crowded) */
+#define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */
 int pf_set_option(pf_handle* h, int option, int value);

@@ -54,6 +54,9 @@ def lib() -> C.CDLL:
         L.po_step_field.restype = None
         L.po_deposit.argtypes = [cfgp, fp, C.c_int64, fp, fp, fp, u8p]
         L.po_deposit.restype = None
+        for name in ("po_deposit_dense", "po_deposit_sorted"):
+            getattr(L, name).argtypes = [cfgp, fp, C.c_int64, fp, fp, fp, u8p]
+            getattr(L, name).restype = None
         L.po_agents_deposit.argtypes = [cfgp, fp, C.c_int64, fp, fp, u32p]
         L.po_agents_deposit.restype = C.c_int64
         L.po_sense.argtypes = [cfgp, fp, C.c_int64, fp, fp, fp, u32p, fp]
@@ -187,12 +190,12 @@ class DenseOracle:
                                 _fp(self.bufs[self.cur ^ 1]))
             self.cur ^= 1
 
-    def deposit(self, x, y, amount, channel=None):
+    def deposit(self, x, y, amount, channel=None, impl="po_deposit"):
         x = np.ascontiguousarray(x, np.float32)
         y = np.ascontiguousarray(y, np.float32)
         amount = np.ascontiguousarray(amount, np.float32)
         ch = None if channel is None else np.ascontiguousarray(channel, np.uint8)
-        lib().po_deposit(C.byref(self.cfg), _fp(self.bufs[self.cur]), len(x), _fp(x), _fp(y),
+        getattr(lib(), impl)(C.byref(self.cfg), _fp(self.bufs[self.cur]), len(x), _fp(x), _fp(y),
                          _fp(amount), _u8(ch))
 
     def agents_deposit(self, a: AgentsNP) -> int:

@@ -249,9 +249,12 @@ void po_step_field(const pf_config* c, const float* cur, float* nxt) {
 
 /* Generic deposit of n amounts. Per touched cell the amounts are summed in input order starting
  * from 0, then the total is added to the cell once: f = f + ((a1 + a2) + a3 ...). Positions
- * outside the arena or outside rows [row0,row1) are skipped. channel may be NULL. */
-void po_deposit(const pf_config* c, float* f, int64_t n, const float* x, const float* y,
-                const float* amount, const uint8_t* channel) {
+ * outside the arena or outside rows [row0,row1) are skipped. channel may be NULL.
+ * Two equivalent implementations (tests/test_oracle_dense.py compares them): a dense accumulator
+ * over all cells, and — for the full-size configs, where a per-call accumulator of 2^31 cells is
+ * not affordable — a stable sort of the deposits by cell followed by the same in-order sums. */
+void po_deposit_dense(const pf_config* c, float* f, int64_t n, const float* x, const float* y,
+                      const float* amount, const uint8_t* channel) {
   po_geom g;
   po_geometry(c, &g);
   int64_t cells = (int64_t)c->C * g.rows * c->W;
@@ -278,6 +281,69 @@ void po_deposit(const pf_config* c, float* f, int64_t n, const float* x, const f
       }
   free(acc);
   free(touched);
+}
+
+void po_deposit_sorted(const pf_config* c, float* f, int64_t n, const float* x, const float* y,
+                       const float* amount, const uint8_t* channel) {
+  po_geom g;
+  po_geometry(c, &g);
+  size_t cap = (size_t)(n > 0 ? n : 1);
+  uint64_t* key = (uint64_t*)malloc(sizeof(uint64_t) * cap);
+  uint64_t* key2 = (uint64_t*)malloc(sizeof(uint64_t) * cap);
+  uint32_t* idx = (uint32_t*)malloc(sizeof(uint32_t) * cap);
+  uint32_t* idx2 = (uint32_t*)malloc(sizeof(uint32_t) * cap);
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int r, q;
+    if (!po_cell(c, &g, x[i], y[i], &r, &q)) continue;
+    if (r < c->row0 || r >= c->row1) continue;
+    int ch = channel ? channel[i] : 0;
+    if (ch < 0 || ch >= c->C) continue;
+    key[m] = (uint64_t)(((int64_t)ch * g.rows + (r - c->row0)) * c->W + q);
+    idx[m] = (uint32_t)i;
+    ++m;
+  }
+  /* stable LSD radix sort by cell, 16 bits a pass: equal cells keep input order */
+  uint64_t maxk = (uint64_t)c->C * (uint64_t)g.rows * (uint64_t)c->W;
+  size_t* cnt = (size_t*)malloc(sizeof(size_t) * 65537);
+  for (int shift = 0; shift < 64 && (maxk >> shift) != 0; shift += 16) {
+    memset(cnt, 0, sizeof(size_t) * 65537);
+    for (int64_t i = 0; i < m; ++i) cnt[((key[i] >> shift) & 0xffffu) + 1]++;
+    for (int b = 0; b < 65536; ++b) cnt[b + 1] += cnt[b];
+    for (int64_t i = 0; i < m; ++i) {
+      size_t d = cnt[(key[i] >> shift) & 0xffffu]++;
+      key2[d] = key[i];
+      idx2[d] = idx[i];
+    }
+    uint64_t* tk = key; key = key2; key2 = tk;
+    uint32_t* ti = idx; idx = idx2; idx2 = ti;
+  }
+  for (int64_t i = 0; i < m;) {
+    float acc = 0.0f;
+    int64_t j = i;
+    while (j < m && key[j] == key[i]) {
+      acc = acc + amount[idx[j]];
+      ++j;
+    }
+    int64_t k = (int64_t)key[i];
+    int64_t plane = (int64_t)g.rows * c->W;
+    int ch = (int)(k / plane);
+    int64_t rem = k - (int64_t)ch * plane;
+    int lr = (int)(rem / c->W);
+    int q = (int)(rem - (int64_t)lr * c->W);
+    float* p = po_at(c, &g, f, ch, lr + c->row0, q);
+    *p = *p + acc;
+    i = j;
+  }
+  free(cnt);
+  free(key); free(key2); free(idx); free(idx2);
+}
+
+void po_deposit(const pf_config* c, float* f, int64_t n, const float* x, const float* y,
+                const float* amount, const uint8_t* channel) {
+  int64_t cells = (int64_t)c->C * (c->row1 - c->row0) * c->W;
+  if (cells > ((int64_t)1 << 26)) po_deposit_sorted(c, f, n, x, y, amount, channel);
+  else po_deposit_dense(c, f, n, x, y, amount, channel);
 }
 
 /* deposit_pheromone over all agents, sup:291-358: gate on the moved flag (sup:308-310); SEARCHING:

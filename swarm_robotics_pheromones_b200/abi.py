@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 
-PF_ABI_VERSION = 1
+PF_ABI_VERSION = 2
 PF_MAX_CHANNELS = 4
 PF_MAX_FOOD = 16
 PF_MIGRATE_WORDS = 8
@@ -29,6 +29,8 @@ META_DEC_MASK = 0x38
 META_CARRY = 0x40
 META_HASPOS = 0x80
 META_COUNT_SHIFT = 8
+META_COUNT_MASK = 0x7FFFFF
+META_HANDED = 0x80000000
 
 OPT_OVERLAP_AGENTS = 1
 OPT_NO_FUSED_KEYS = 2
@@ -36,6 +38,8 @@ OPT_USE_GRAPH = 3
 OPT_NO_OWNER_DEPOSIT = 4
 OPT_FORCE_OWNER_DEPOSIT = 5
 OPT_NO_TILE_DEPOSIT = 6
+OPT_PEER_TIMEOUT_MS = 7
+TICK_A, TICK_B, TICK_C, TICK_ALL = 0x1, 0x2, 0x4, 0x7
 STEP_DEPOSIT, STEP_SENSE, STEP_FIELD, STEP_MOVE, STEP_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 STEP_HANDOVER = 0x10  # pf_agents_step on a strip: interior rows hand their next deposit to the stencil
 
@@ -98,6 +102,7 @@ class PFConfig(C.Structure):
         ("dt", C.c_float),
         ("wheel_radius", C.c_float),
         ("axle_length", C.c_float),
+        ("migrate_cap", C.c_int32),
     ]
 
     def copy(self) -> "PFConfig":
@@ -132,6 +137,7 @@ class PFCounters(C.Structure):
         ("migrated_out", C.c_uint64),
         ("migrated_in", C.c_uint64),
         ("migrate_dropped", C.c_uint64),
+        ("peer_timeouts", C.c_uint64),
     ]
 
 
@@ -144,7 +150,8 @@ class PFTrailOut(C.Structure):
 
 class PFPeerInfo(C.Structure):
     _fields_ = [("buf0", C.c_void_p), ("buf1", C.c_void_p), ("flags", C.c_void_p),
-                ("rows", C.c_int64), ("pitch", C.c_int64), ("chan_stride", C.c_int64)]
+                ("rows", C.c_int64), ("pitch", C.c_int64), ("chan_stride", C.c_int64),
+                ("mig", C.c_void_p), ("mig_cap", C.c_int64)]
 
 
 class PFProfile(C.Structure):
@@ -213,6 +220,7 @@ def default_config(H: int, W: int, C_: int = 1, *, cell_size: float = 0.01, devi
     c.dt = 0.064
     c.wheel_radius = 0.02
     c.axle_length = 0.052
+    c.migrate_cap = 0
     return c
 
 
@@ -226,7 +234,7 @@ def meta_state(m):
 
 
 def meta_count(m):
-    return m >> META_COUNT_SHIFT
+    return (m >> META_COUNT_SHIFT) & META_COUNT_MASK
 
 
 def meta_decision(m):

@@ -36,15 +36,20 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
     uint32_t st = mt & PF_META_STATE_MASK;
     uint32_t key = sentinel;
     float amt = 0.0f;
-    if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && (mt & PF_META_MOVED)) {
+    // the move kernel marked the robots whose deposit it handed to the stencil (PF_META_HANDED): the
+    // mark, not the position, says who they are — poses may have been replaced since (pf_agents_observe)
+    const bool was_handed = (mt & PF_META_HANDED) != 0u;
+    if (was_handed) {
+      mt &= ~PF_META_HANDED;
+      meta[i] = mt;
+    }
+    if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && ((mt & PF_META_MOVED) || was_handed)) {
       int r, q;
       bool inside = pf_cell(p, x[i], y[i], r, q);
       int ch = p.dep_ch[st];
       const bool mine = inside && r >= p.row0 && r < p.row1;
-      uint32_t local;
-      const bool was_handed = handed.bcnt && mine && tile_of(handed, ch, r - p.row0, q, &local) >= 0;
       if (!(was_handed && handed_done)) {
-        uint32_t cnt = (mt >> PF_META_COUNT_SHIFT) + (was_handed ? 0u : 1u);
+        uint32_t cnt = ((mt >> PF_META_COUNT_SHIFT) + (was_handed ? 0u : 1u)) & PF_META_COUNT_MASK;
         amt = (st == PF_STATE_SEARCHING)
                   ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
                   : p.i_homing;
@@ -396,10 +401,11 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
           const bool mine = inside && r >= p.row0 && r < p.row1;
           if (mine && tb.bcnt) tile = tile_of(tb, p.dep_ch[st], r - p.row0, q, &local);
           if (next_keys || tile >= 0) {
-            uint32_t cnt = (nm >> PF_META_COUNT_SHIFT) + 1u;
+            uint32_t cnt = ((nm >> PF_META_COUNT_SHIFT) + 1u) & PF_META_COUNT_MASK;
             amt = (st == PF_STATE_SEARCHING) ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
                                              : p.i_homing;
             nm = (nm & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
+            if (!next_keys) nm |= PF_META_HANDED;  // strips: the next key kernel skips this robot (or deposits it after all)
             if (mine) key = (uint32_t)(((long long)p.dep_ch[st] * p.rows + (r - p.row0)) * p.W + q);
             atomicAdd(&hist[8], 1u);
           }
@@ -712,19 +718,27 @@ __global__ void k_peer_push_edges(PFDev p, const float* __restrict__ f, PeerRows
   if (peer.dn) peer.dn[ch * peer.dn_cs + col] = plane[(long long)p.rows * p.pitch + col];
 }
 
-// after the wait: the rows the neighbours stored into this strip's mailbox become its ghost rows
-__global__ void k_mailbox_to_ghosts(PFDev p, float* f, const float* __restrict__ mailbox, int top, int bottom) {
-  int col = blockIdx.x * blockDim.x + threadIdx.x;
-  int ch = blockIdx.y;
-  if (col >= p.W) return;
-  float* plane = f + (long long)ch * p.chan_stride;
-  if (top) plane[col] = mailbox[(long long)ch * p.pitch + col];
-  if (bottom) plane[(long long)(p.rows + 1) * p.pitch + col] = mailbox[(long long)(p.C + ch) * p.pitch + col];
-}
-
 // Epoch flags in the RECEIVER's memory: a strip stores `epoch` into its neighbours' flag words after
-// its deposit; each strip polls its own two words before it reads its ghost rows. One thread each;
-// between different GPUs (or, for in-process strips on one GPU, already satisfied by stream order).
+// its deposit (halo) / after packing its leavers (migration); each strip polls its own words before it
+// reads what the neighbours stored. The poll is bounded: a neighbour that has not signalled after
+// `limit_ns` (dead rank, strips out of lockstep) is counted in counters[13] (pf_counters.peer_timeouts,
+// pf_peer_status) and the kernel goes on instead of wedging the stream.
+__device__ __forceinline__ unsigned long long pf_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool peer_spin(volatile const unsigned int* w, unsigned int epoch, unsigned long long limit_ns) {
+  if ((int)(*w - epoch) >= 0) return true;
+  const unsigned long long t0 = pf_globaltimer();
+  unsigned ns = 32;
+  while ((int)(*w - epoch) < 0) {
+    __nanosleep(ns);
+    if (ns < 2048) ns *= 2;
+    if (pf_globaltimer() - t0 > limit_ns) return false;
+  }
+  return true;
+}
 __global__ void k_peer_signal(volatile unsigned int* up_flag, volatile unsigned int* dn_flag, unsigned int epoch) {
   __threadfence_system();
   if (up_flag) *up_flag = epoch;
@@ -732,10 +746,32 @@ __global__ void k_peer_signal(volatile unsigned int* up_flag, volatile unsigned 
   __threadfence_system();
 }
 __global__ void k_peer_wait(volatile const unsigned int* from_up, volatile const unsigned int* from_dn,
-                            unsigned int epoch) {
-  if (from_up) while ((int)(*from_up - epoch) < 0) { }
-  if (from_dn) while ((int)(*from_dn - epoch) < 0) { }
+                            unsigned int epoch, unsigned long long limit_ns, unsigned long long* counters) {
+  bool ok = true;
+  if (from_up) ok = peer_spin(from_up, epoch, limit_ns) && ok;
+  if (from_dn) ok = peer_spin(from_dn, epoch, limit_ns) && ok;
+  if (!ok) atomicAdd(&counters[13], 1ull);
   __threadfence_system();
+}
+// halo wait + the rows the neighbours stored into this strip's mailbox become its ghost rows
+__global__ void __launch_bounds__(256)
+k_peer_wait_ghosts(PFDev p, float* f, const float* mailbox, volatile const unsigned int* from_up,
+                   volatile const unsigned int* from_dn, unsigned int epoch, unsigned long long limit_ns,
+                   unsigned long long* counters) {
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    if (from_up) ok = peer_spin(from_up, epoch, limit_ns) && ok;
+    if (from_dn) ok = peer_spin(from_dn, epoch, limit_ns) && ok;
+    if (!ok && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&counters[13], 1ull);
+    __threadfence_system();
+  }
+  __syncthreads();
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  int ch = blockIdx.y;
+  if (col >= p.W) return;
+  float* plane = f + (long long)ch * p.chan_stride;
+  if (from_up) plane[col] = __ldcg(mailbox + (long long)ch * p.pitch + col);
+  if (from_dn) plane[(long long)(p.rows + 1) * p.pitch + col] = __ldcg(mailbox + (long long)(p.C + ch) * p.pitch + col);
 }
 
 __global__ void k_fill_ghosts(PFDev p, float* f, int top, int bottom) {

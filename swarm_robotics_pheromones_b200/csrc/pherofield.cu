@@ -79,9 +79,17 @@ struct pf_handle {
   int own_worth;              // host heuristic from the last pf_agents_sort (see there)
   double own_scan_estimate;
   // peer-store halo (NVLink P2P): neighbours' buffers / flag words, mapped into this process
-  struct PeerLink { float* buf[2]; unsigned int* flags; long long rows, pitch, chan_stride; int set; } peer_up, peer_dn;
-  unsigned int* peer_flags;  // device: [0] written by the strip above, [1] by the strip below
-  unsigned int peer_epoch;
+  struct PeerLink { float* buf[2]; unsigned int* flags; long long rows, pitch, chan_stride; int set;
+                    uint32_t* mig; long long mig_cap; } peer_up, peer_dn;
+  unsigned int* peer_flags;  // device: halo epochs [0] written by the strip above, [1] by the strip below; migration [2], [3]
+  unsigned int peer_epoch, mig_epoch;
+  long long mig_cap;         // records per direction the migration mailbox (and the dummy send buffers) take
+  uint32_t* mig_dummy;       // send target on a side without a neighbour (walls reflect: stays empty)
+  void* ipc_opened[4];       // cudaIpcOpenMemHandle mappings to close in pf_destroy
+  int n_ipc;
+  unsigned long long peer_timeout_ns;
+  int strip_dep0, strip_dep1;  // pf_strip_tick: rows handed over this tick (phase A decides, B and C use)
+  bool strip_active;
   long long mig_flags_n;   // > 0: mig_cnt holds the per-chunk leaver counts the last move kernel made
   const float* mig_flags_x;
   uint32_t *mig_cnt, *mig_base, *emp_cnt, *emp_base;  // per chunk (two-level migration, pf_agents.cuh)
@@ -126,6 +134,12 @@ static int set_err(pf_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 static bool is_sharded(const pf_handle* h) { return h->cfg.row0 > 0 || h->cfg.row1 < h->cfg.H; }
+static long long mig_cap_of(const pf_config* c) { return c->migrate_cap > 0 ? c->migrate_cap : 16384; }
+// byte offset of the migration mailbox inside the peer block: behind the flag words and the halo rows
+static size_t mig_offset(int C, long long pitch) {
+  return (256 + sizeof(float) * 4 * (size_t)C * (size_t)pitch + 255) & ~(size_t)255;
+}
+static size_t mig_box_words(long long cap) { return (size_t)(cap + 1) * PF_MIGRATE_WORDS; }
 static void graph_drop(pf_handle* h);
 
 static void tile_free(pf_handle* h) {
@@ -226,6 +240,7 @@ static int validate(const pf_config* c) {
       return set_err(nullptr, PF_EINVAL, "sharded field: sense_dist must be <= cell_size");
     }
   }
+  if (c->migrate_cap < 0 || c->migrate_cap > (1 << 24)) return set_err(nullptr, PF_EINVAL, "migrate_cap out of range");
   unsigned long long cells = (unsigned long long)c->C * (unsigned long long)(c->row1 - c->row0) * (unsigned long long)c->W;
   if (cells >= 0xffffffffull) return set_err(nullptr, PF_EINVAL, "more than 2^32-1 cells per handle: shard the field");
   return PF_OK;
@@ -313,9 +328,14 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
   {  // peer mailbox block: 256 B of flag words + [2 buffer parities][2 sides][C][pitch] floats. Neighbour strips
      // store edge rows here (small, IPC-mapped) rather than into the field allocation itself: mapping the
      // multi-GB field for peer access cost the stencil 40 % (measured), presumably through smaller pages
-    const size_t bytes = 256 + sizeof(float) * 4 * (size_t)cfg->C * h->dev.pitch;
+    // ... followed by the migration mailbox: two record buffers the neighbours pack their leavers into
+    h->mig_cap = mig_cap_of(cfg);
+    const size_t bytes = mig_offset(cfg->C, h->dev.pitch) + 2 * sizeof(uint32_t) * mig_box_words(h->mig_cap);
     CREATE_CUDA(cudaMalloc(&h->peer_flags, bytes));
     CREATE_CUDA(cudaMemset(h->peer_flags, 0, bytes));
+    CREATE_CUDA(cudaMalloc(&h->mig_dummy, sizeof(uint32_t) * mig_box_words(h->mig_cap)));
+    CREATE_CUDA(cudaMemset(h->mig_dummy, 0, sizeof(uint32_t) * mig_box_words(h->mig_cap)));
+    h->peer_timeout_ns = 5000000000ull;  // a neighbour that does not signal within 5 s is counted as dead
   }
   {
     int lo = 0, hi = 0;  // the side stream outranks the caller's: its small kernels are not starved
@@ -366,7 +386,9 @@ extern "C" int pf_destroy(pf_handle* h) {
   tile_free(h);
   if (h->counters) cudaFree(h->counters);
   if (h->d_sum) cudaFree(h->d_sum);
+  for (int k = 0; k < h->n_ipc; ++k) cudaIpcCloseMemHandle(h->ipc_opened[k]);
   if (h->peer_flags) cudaFree(h->peer_flags);
+  if (h->mig_dummy) cudaFree(h->mig_dummy);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -458,6 +480,10 @@ extern "C" int pf_field_upload_host(pf_handle* h, int channel, const float* src,
 
 extern "C" int pf_snapshot_host(pf_handle* h, int channel, float* dst, void* stream) {
   if (!h || !dst || channel < 0 || channel >= h->cfg.C) return PF_EINVAL;
+  if (h->tile_handed || h->tile_pending)
+    return set_err(h, PF_ESTATE, "%s after a hand-over tick (PF_STEP_HANDOVER): the interior rows and the deposit "
+                                 "counters already hold the NEXT tick's deposits; run the last tick before reading "
+                                 "without PF_STEP_HANDOVER", "pf_snapshot_host");
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   const float* src = h->buf[h->cur] + (long long)channel * h->dev.chan_stride + h->dev.pitch;
   PF_CUDA(h, cudaMemcpy2DAsync(dst, sizeof(float) * h->cfg.W, src, sizeof(float) * h->dev.pitch,
@@ -491,6 +517,10 @@ struct RowSumOp {
 
 extern "C" int pf_field_sum_host(pf_handle* h, int channel, double* sum_host, void* stream) {
   if (!h || !sum_host || channel < 0 || channel >= h->cfg.C) return PF_EINVAL;
+  if (h->tile_handed || h->tile_pending)
+    return set_err(h, PF_ESTATE, "%s after a hand-over tick (PF_STEP_HANDOVER): the interior rows and the deposit "
+                                 "counters already hold the NEXT tick's deposits; run the last tick before reading "
+                                 "without PF_STEP_HANDOVER", "pf_field_sum_host");
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   RowSumOp op{h->buf[h->cur] + (long long)channel * h->dev.chan_stride + h->dev.pitch, h->dev.pitch, h->cfg.W};
@@ -646,6 +676,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_NO_TILE_DEPOSIT) { h->no_tile_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_OWNER_DEPOSIT) { h->no_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_FORCE_OWNER_DEPOSIT) { h->force_owner_deposit = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
 }
@@ -1323,12 +1354,18 @@ extern "C" int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32
 // ---------------------------------------------------------------------------------------------
 // peer-store halo (NVLink P2P)
 // ---------------------------------------------------------------------------------------------
+static uint32_t* mig_box_of(unsigned int* flags_base, int side, int C, long long pitch, long long cap) {
+  return (uint32_t*)((char*)flags_base + mig_offset(C, pitch)) + (size_t)side * mig_box_words(cap);
+}
+
 extern "C" int pf_peer_export(pf_handle* h, pf_peer_info* out) {
   if (!h || !out) return PF_EINVAL;
   out->buf0 = mailbox_of(h->peer_flags, 0, h->cfg.C, h->dev.pitch);
   out->buf1 = mailbox_of(h->peer_flags, 1, h->cfg.C, h->dev.pitch);
   out->flags = h->peer_flags;
   out->rows = h->dev.rows; out->pitch = h->dev.pitch; out->chan_stride = h->dev.chan_stride;
+  out->mig = mig_box_of(h->peer_flags, 0, h->cfg.C, h->dev.pitch, h->mig_cap);
+  out->mig_cap = h->mig_cap;
   return PF_OK;
 }
 
@@ -1346,15 +1383,18 @@ extern "C" int pf_peer_ipc_handles(pf_handle* h, uint8_t* out192) {
 // map a neighbour process's buffers into this process; `dims` = that neighbour's pf_peer_export
 extern "C" int pf_peer_ipc_open(pf_handle* h, const uint8_t* in192, const pf_peer_info* dims, pf_peer_info* out) {
   if (!h || !in192 || !dims || !out) return PF_EINVAL;
+  if (h->n_ipc >= 4) return set_err(h, PF_ESTATE, "pf_peer_ipc_open: more than 4 mappings on one handle");
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   void* base = nullptr;
   cudaIpcMemHandle_t mh;
   memcpy(&mh, in192, 64);
   PF_CUDA(h, cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->ipc_opened[h->n_ipc++] = base;
   *out = *dims;
   out->flags = base;
   out->buf0 = mailbox_of((unsigned int*)base, 0, h->cfg.C, dims->pitch);
   out->buf1 = mailbox_of((unsigned int*)base, 1, h->cfg.C, dims->pitch);
+  out->mig = dims->mig_cap > 0 ? mig_box_of((unsigned int*)base, 0, h->cfg.C, dims->pitch, dims->mig_cap) : nullptr;
   return PF_OK;
 }
 
@@ -1367,6 +1407,7 @@ extern "C" int pf_peer_attach(pf_handle* h, const pf_peer_info* up, const pf_pee
     if (!i) return;
     l.buf[0] = (float*)i->buf0; l.buf[1] = (float*)i->buf1; l.flags = (unsigned int*)i->flags;
     l.rows = i->rows; l.pitch = i->pitch; l.chan_stride = i->chan_stride; l.set = 1;
+    l.mig = (uint32_t*)i->mig; l.mig_cap = i->mig_cap;
   };
   set(h->peer_up, up);
   set(h->peer_dn, down);
@@ -1399,15 +1440,127 @@ extern "C" int pf_peer_wait(pf_handle* h, void* stream) {
   if (!h) return PF_EINVAL;
   if (!h->peer_up.set && !h->peer_dn.set) return PF_OK;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
-  k_peer_wait<<<1, 1, 0, (cudaStream_t)stream>>>(h->peer_up.set ? h->peer_flags + 0 : nullptr,
-                                                h->peer_dn.set ? h->peer_flags + 1 : nullptr, h->peer_epoch);
-  PF_LAUNCH_CHECK(h);
-  // mailbox of the current buffer -> this strip's ghost rows
+  // every CTA polls this strip's own two epoch words (bounded), then copies its columns of the
+  // mailbox rows of the current buffer into the ghost rows
   dim3 grid(blocks_for(h->cfg.W, 256), h->cfg.C);
-  k_mailbox_to_ghosts<<<grid, 256, 0, (cudaStream_t)stream>>>(h->dev, h->buf[h->cur],
-                                                            mailbox_of(h->peer_flags, h->cur, h->cfg.C, h->dev.pitch),
-                                                            h->peer_up.set, h->peer_dn.set);
+  k_peer_wait_ghosts<<<grid, 256, 0, (cudaStream_t)stream>>>(h->dev, h->buf[h->cur],
+                                                           mailbox_of(h->peer_flags, h->cur, h->cfg.C, h->dev.pitch),
+                                                           h->peer_up.set ? h->peer_flags + 0 : nullptr,
+                                                           h->peer_dn.set ? h->peer_flags + 1 : nullptr,
+                                                           h->peer_epoch, h->peer_timeout_ns, h->counters);
   PF_LAUNCH_CHECK(h);
+  return PF_OK;
+}
+
+extern "C" int pf_peer_status(pf_handle* h, void* stream) {
+  if (!h) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  unsigned long long t = 0;
+  PF_CUDA(h, cudaMemcpyAsync(&t, h->counters + 13, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PF_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  if (t)
+    return set_err(h, PF_ESTATE, "%llu peer wait(s) timed out: a neighbour strip did not signal (dead rank, or the "
+                                 "strips are not ticking in lockstep); field and agents are not valid", t);
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one strip tick by one call (no host round trips between the phases)
+// ---------------------------------------------------------------------------------------------
+// Leavers are packed straight into the neighbours' migration mailboxes (peer stores), followed by an
+// epoch flag — the halo's protocol once more. One mailbox per direction is enough: the neighbour's
+// next pack comes behind its halo wait of the next tick, which needs this strip's halo signal, which
+// this strip enqueues behind its unpack (same stream).
+static int strip_pack(pf_handle* h, const pf_agents* a, cudaStream_t s) {
+  uint32_t* up = h->peer_up.set && h->peer_up.mig ? h->peer_up.mig + mig_box_words(h->peer_up.mig_cap) : h->mig_dummy;
+  uint32_t* dn = h->peer_dn.set && h->peer_dn.mig ? h->peer_dn.mig : h->mig_dummy;
+  long long cap = h->mig_cap;
+  if (h->peer_up.set && h->peer_up.mig_cap < cap) cap = h->peer_up.mig_cap;
+  if (h->peer_dn.set && h->peer_dn.mig_cap < cap) cap = h->peer_dn.mig_cap;
+  int rc = pf_migrate_pack(h, a, up, dn, cap, (void*)s);
+  if (rc) return rc;
+  h->mig_epoch += 1;
+  if (h->peer_up.set || h->peer_dn.set) {
+    k_peer_signal<<<1, 1, 0, s>>>(h->peer_up.set ? h->peer_up.flags + 3 : nullptr,
+                                  h->peer_dn.set ? h->peer_dn.flags + 2 : nullptr, h->mig_epoch);
+    PF_LAUNCH_CHECK(h);
+  }
+  return PF_OK;
+}
+
+static int strip_unpack(pf_handle* h, const pf_agents* a, cudaStream_t s) {
+  if (!h->peer_up.set && !h->peer_dn.set) return PF_OK;
+  k_peer_wait<<<1, 1, 0, s>>>(h->peer_up.set ? h->peer_flags + 2 : nullptr, h->peer_dn.set ? h->peer_flags + 3 : nullptr,
+                              h->mig_epoch, h->peer_timeout_ns, h->counters);
+  PF_LAUNCH_CHECK(h);
+  uint32_t* from_up = h->peer_up.set ? mig_box_of(h->peer_flags, 0, h->cfg.C, h->dev.pitch, h->mig_cap) : nullptr;
+  uint32_t* from_dn = h->peer_dn.set ? mig_box_of(h->peer_flags, 1, h->cfg.C, h->dev.pitch, h->mig_cap) : nullptr;
+  return pf_migrate_unpack2(h, a, from_up, from_dn, h->mig_cap, (void*)s);
+}
+
+extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, uint32_t phases, void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (!(phases & PF_TICK_ALL)) return set_err(h, PF_EINVAL, "pf_strip_tick: no phase selected");
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dep = (flags & PF_STEP_DEPOSIT) != 0, move = (flags & PF_STEP_MOVE) != 0;
+  const int rows = h->dev.rows;
+  if (a->n > 0) { rc = pf_reserve_agents(h, a->n); if (rc) return rc; }
+  if (phases & PF_TICK_A) {  // deposit, halo signal
+    if (h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase A twice (phases must run A, B, C)");
+    h->strip_dep0 = h->strip_dep1 = 0;
+    if ((flags & PF_STEP_HANDOVER) && dep && move && (flags & PF_STEP_SENSE) && a->n > 0) {
+      int ty0, ty1;
+      if (strip_tile_range(h, a, &ty0, &ty1)) {
+        h->strip_dep0 = ty0 * kTileRows;
+        h->strip_dep1 = ty1 * kTileRows < rows ? ty1 * kTileRows : rows;
+      }
+    }
+    if (dep && a->n > 0) { rc = pf_agents_deposit(h, a, stream); if (rc) return rc; }
+    rc = pf_peer_signal(h, stream);
+    if (rc) return rc;
+    h->strip_active = true;
+  }
+  const int lo = 1, hi = rows - 1 > 1 ? rows - 1 : 1;
+  const bool handing = h->strip_dep1 > h->strip_dep0;
+  const int mid = handing ? h->strip_dep0 : lo + (hi - lo) / 2;
+  if (phases & PF_TICK_B) {  // interior rows while the halo is in flight, halo wait, agents, leavers out
+    if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase B without phase A");
+    if (mid > lo) { rc = launch_stencil(h, lo, mid, s); if (rc) return rc; }
+    rc = pf_peer_wait(h, stream);
+    if (rc) return rc;
+    if (a->n > 0 && (flags & (PF_STEP_SENSE | PF_STEP_MOVE))) {
+      const uint32_t f = (flags & (PF_STEP_SENSE | PF_STEP_MOVE)) | (handing ? PF_STEP_HANDOVER : 0u);
+      rc = pf_agents_step(h, a, f, nullptr, stream);
+      if (rc) return rc;
+      if (handing && !h->tile_pending) return set_err(h, PF_ESTATE, "pf_strip_tick: hand-over range changed inside a tick");
+    }
+    if (move) { rc = strip_pack(h, a, s); if (rc) return rc; }
+  }
+  if (phases & PF_TICK_C) {  // the remaining rows (deposits riding along), swap, arrivals in
+    if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase C without phase A");
+    bool last_done = false;
+    if (handing) {
+      rc = pf_step_field_rows(h, h->strip_dep0, h->strip_dep1, stream);  // exactly these rows: the deposits ride along
+      if (rc) return rc;
+      last_done = true;
+      if (h->strip_dep1 < rows) { rc = launch_stencil(h, h->strip_dep1, rows, s); if (rc) return rc; }
+    } else if (hi > mid) {
+      rc = launch_stencil(h, mid, hi, s);
+      if (rc) return rc;
+    }
+    rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
+    if (rc) return rc;
+    if (rows > 1 && !last_done) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
+    rc = pf_swap(h);
+    if (rc) return rc;
+    if (move) { rc = strip_unpack(h, a, s); if (rc) return rc; }
+    k_tick_counter<<<1, 1, 0, s>>>(h->counters);
+    PF_LAUNCH_CHECK(h);
+    h->strip_active = false;
+    h->strip_dep0 = h->strip_dep1 = 0;
+  }
   return PF_OK;
 }
 
@@ -1416,6 +1569,10 @@ extern "C" int pf_peer_wait(pf_handle* h, void* stream) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int pf_counters_host(pf_handle* h, pf_counters* out, void* stream) {
   if (!h || !out) return PF_EINVAL;
+  if (h->tile_handed || h->tile_pending)
+    return set_err(h, PF_ESTATE, "%s after a hand-over tick (PF_STEP_HANDOVER): the interior rows and the deposit "
+                                 "counters already hold the NEXT tick's deposits; run the last tick before reading "
+                                 "without PF_STEP_HANDOVER", "pf_counters_host");
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   unsigned long long c[16];
   PF_CUDA(h, cudaMemcpyAsync(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -1428,6 +1585,7 @@ extern "C" int pf_counters_host(pf_handle* h, pf_counters* out, void* stream) {
   out->migrated_out = c[10];
   out->migrated_in = c[11];
   out->migrate_dropped = c[12];
+  out->peer_timeouts = c[13];
   return PF_OK;
 }
 

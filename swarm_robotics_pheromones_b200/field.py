@@ -280,6 +280,14 @@ class PheroField:
     def peer_wait(self):
         self._ck(self._L.pf_peer_wait(self._h, self._s()))
 
+    def peer_status(self):
+        """raises PFError(PF_ESTATE) if a bounded peer wait gave up (dead neighbour / strips out of lockstep)"""
+        self._ck(self._L.pf_peer_status(self._h, self._s()))
+
+    def strip_tick(self, a: Swarm, flags: int, phases: int = abi.TICK_ALL):
+        """one whole strip tick by one C call (pf_strip_tick): leavers travel through the peer mailboxes"""
+        self._ck(self._L.pf_strip_tick(self._h, C.byref(a.struct()), flags, phases, self._s()))
+
     # -- counters / tuning
     def counters(self) -> abi.PFCounters:
         c = abi.PFCounters()

@@ -57,6 +57,8 @@ class CudaStrip:
 
     def __init__(self, cfg: abi.PFConfig, x, y, theta, state, gid, capacity: int, migrate_cap: int):
         from .field import PheroField, Swarm
+        cfg = cfg.copy()
+        cfg.migrate_cap = migrate_cap  # the peer mailbox the neighbours pack their leavers into (pf_strip_tick)
         self.cfg = cfg
         self.field = PheroField(cfg)
         self.swarm = Swarm(x, y, theta, state, device=self.field.device, capacity=capacity, gid=gid)
@@ -139,16 +141,17 @@ class CudaStrip:
         the two neighbour ranks and map them (cudaIpcOpenMemHandle enables NVLink peer access)"""
         import torch.distributed as dist
         info = self.field.peer_export()
-        mine = (self.field.peer_ipc_handles(), int(info.rows), int(info.pitch), int(info.chan_stride))
+        mine = (self.field.peer_ipc_handles(), int(info.rows), int(info.pitch), int(info.chan_stride),
+                int(info.mig_cap))
         everyone = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
 
         def opened(r):
             if r < 0 or r >= world:
                 return None
-            handles, rows, pitch, cs = everyone[r]
+            handles, rows, pitch, cs, mig_cap = everyone[r]
             dims = abi.PFPeerInfo()
-            dims.rows, dims.pitch, dims.chan_stride = rows, pitch, cs
+            dims.rows, dims.pitch, dims.chan_stride, dims.mig_cap = rows, pitch, cs, mig_cap
             return self.field.peer_ipc_open(handles, dims)
 
         self.field.peer_attach(opened(rank - 1), opened(rank + 1))
@@ -164,6 +167,11 @@ class CudaStrip:
 
     def peer_wait(self):
         self.field.peer_wait()
+
+    def strip_tick(self, flags: int, phases: int = abi.TICK_ALL):
+        """the whole tick by one C call (pf_strip_tick); needs the peers attached (their mailboxes take the
+        leavers). Used by DistDriver / LocalDriver whenever `peer` is set."""
+        self.field.strip_tick(self.swarm, flags, phases)
 
 
 class StripWorker:
@@ -312,7 +320,18 @@ class LocalDriver:
 
     peer = False
 
-    def tick(self, sense_enabled: bool = True, hand_over: bool = True):
+    def tick(self, sense_enabled: bool = True, hand_over: bool = False):
+        """hand_over=True lets the interior rows' NEXT deposits ride on this tick's stencil: only when another
+        depositing tick follows before the field, the counters or the agents are read or re-sorted (run() decides
+        this by itself)."""
+        if self.peer and all(hasattr(w.b, "strip_tick") for w in self.w):
+            flags = strip_flags(sense_enabled, True, hand_over)
+            for phase in (abi.TICK_A, abi.TICK_B, abi.TICK_C):  # one stream: every strip's signal before any wait
+                for w in self.w:
+                    w.b.strip_tick(flags, phase)
+            for w in self.w:
+                w.ticks += 1
+            return
         for w in self.w:
             w.begin_tick(hand_over and sense_enabled)
             w.deposit(sense_enabled)
@@ -338,9 +357,13 @@ class DistDriver:
     The halo travels on a side stream while the interior rows' stencil runs; only the two edge
     rows and the agent step wait for it."""
 
-    def __init__(self, worker: StripWorker, group=None, overlap: bool = True, profile: bool = False):
+    def __init__(self, worker: StripWorker, group=None, overlap: bool = True, profile: bool = False,
+                 legacy: bool = False):
+        """legacy=True keeps the phase-by-phase host loop with NCCL migration (the round-1 path; also what
+        profile=True uses, for its per-phase events)"""
         import torch.distributed as dist
         self.profile = profile
+        self.legacy = legacy
         self._marks = []  # per tick: list of (label, event) on the main stream
         self.dist = dist
         self.w = worker
@@ -377,10 +400,17 @@ class DistDriver:
                 r.wait()
             ev_after.record(self.comm_stream)
 
-    def tick(self, sense_enabled: bool = True, move: bool = True, hand_over: bool = True):
+    def tick(self, sense_enabled: bool = True, move: bool = True, hand_over: bool = False):
         """move=False: the caller owns the poses (pf_agents_observe); nothing migrates.
-        hand_over=False: on the tick before a re-sort (pf_agents_sort) or before a tick without deposit"""
+        hand_over=True lets the interior rows' NEXT deposits ride on this tick's stencil: only when another
+        depositing tick follows before the field, the counters or the agents are read or re-sorted (run() decides
+        this by itself)."""
         w = self.w
+        if getattr(w.b, "peer", False) and hasattr(w.b, "strip_tick") and not self.profile and not self.legacy:
+            # one C call enqueues the whole tick; halo rows and leavers cross as peer stores + epoch flags
+            w.b.strip_tick(strip_flags(sense_enabled, move, hand_over))
+            w.ticks += 1
+            return
         w.begin_tick(hand_over and sense_enabled and move)
         marks = [] if (self.profile and self.cuda) else None
 
@@ -457,6 +487,31 @@ class DistDriver:
             w.unpack()
         else:
             w.ticks += 1
+
+
+def strip_flags(sense_enabled: bool, move: bool, hand_over: bool) -> int:
+    """pf_strip_tick flags of a tick (deposit and sensing start together, sup:581)"""
+    f = abi.STEP_FIELD
+    if sense_enabled:
+        f |= abi.STEP_DEPOSIT | abi.STEP_SENSE
+    if move:
+        f |= abi.STEP_MOVE
+    if hand_over and sense_enabled and move:
+        f |= abi.STEP_HANDOVER
+    return f
+
+
+def run_ticks(driver, nticks: int, sort_every: int = 0, sort=None, sense_enabled: bool = True,
+              hand_over: bool = True, tick0: int = 0):
+    """`nticks` ticks of a LocalDriver / DistDriver with the hand-over decided here: never on the last tick (the
+    caller may read the field afterwards) nor on the tick before a re-sort. `sort()` re-orders the agents
+    (strip.sort_agents on every strip) every `sort_every` ticks, counted from `tick0`."""
+    for k in range(nticks):
+        t = tick0 + k
+        if sort is not None and sort_every > 0 and t % sort_every == 0:
+            sort()
+        before_sort = sort is not None and sort_every > 0 and (t + 1) % sort_every == 0
+        driver.tick(sense_enabled, hand_over=hand_over and not before_sort and k + 1 < nticks)
 
 
 def phase_means(driver: "DistDriver", skip: int = 3):

@@ -133,3 +133,56 @@ def test_strip_hand_over_falls_back_when_an_interior_tile_is_crowded():
     assert s1 == (nticks - 1, 0), s1              # its neighbour: none did
     for w in workers:
         w.b.field.close()
+
+
+def test_peer_wait_is_bounded_and_reports_a_dead_neighbour():
+    # strip 0 ticks alone: its neighbour never signals. The wait gives up after the configured bound instead of
+    # wedging the stream, and pf_peer_status / pf_counters report it
+    from swarm_robotics_pheromones_b200._ffi import PFError
+    cfg, x, y, th, st = _scenario(seed=3, n=2000, H=128, W=256, C=1)
+    parts = sharded.partition_agents(cfg, 2, x, y, th, st)
+    strips = [sharded.CudaStrip(sharded.strip_config(cfg, 2, r), parts[r]["x"], parts[r]["y"], parts[r]["theta"],
+                                parts[r]["state"], parts[r]["gid"], capacity=3000, migrate_cap=256) for r in range(2)]
+    strips[0].peer_attach_local(None, strips[1])
+    strips[1].peer_attach_local(strips[0], None)
+    strips[0].field.set_option(abi.OPT_PEER_TIMEOUT_MS, 50)
+    strips[0].field.peer_status()                       # nothing yet
+    strips[0].strip_tick(sharded.strip_flags(True, True, False))
+    torch.cuda.synchronize()
+    with pytest.raises(PFError) as e:
+        strips[0].field.peer_status()
+    assert e.value.code == abi.PF_ESTATE and "timed out" in str(e.value)
+    assert strips[0].field.counters().peer_timeouts >= 1
+    for s_ in strips:
+        s_.field.close()
+
+
+def test_snapshot_and_counters_refuse_the_state_after_a_hand_over_tick():
+    # after a hand-over tick the interior rows and the deposit counters are one tick ahead; reading
+    # them is refused until a tick without PF_STEP_HANDOVER has run
+    from swarm_robotics_pheromones_b200._ffi import PFError
+    cfg, x, y, th, st = _scenario(seed=21, n=14000, H=768, W=512, C=2)
+    parts = sharded.partition_agents(cfg, 2, x, y, th, st)
+    workers = []
+    for r in range(2):
+        p = parts[r]
+        strip = sharded.CudaStrip(sharded.strip_config(cfg, 2, r), p["x"], p["y"], p["theta"], p["state"], p["gid"],
+                                  capacity=14000, migrate_cap=1024)
+        strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
+        workers.append(sharded.StripWorker(strip, r, 2))
+    drv = sharded.LocalDriver(workers)
+    drv.attach_peers()
+    for w in workers:
+        w.b.sort_agents()
+    drv.tick(True, hand_over=True)
+    with pytest.raises(PFError):
+        workers[0].b.field.snapshot()
+    with pytest.raises(PFError):
+        workers[0].b.field.counters()
+    with pytest.raises(PFError):
+        workers[0].b.sort_agents()
+    drv.tick(True)                                      # default: no hand-over
+    workers[0].b.field.snapshot()
+    workers[0].b.field.counters()
+    for w in workers:
+        w.b.field.close()

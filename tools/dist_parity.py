@@ -2,7 +2,12 @@
 GPU, bit for bit (field and agents by gid).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/dist_parity.py --ticks 100
+        --master-port 29511 tools/dist_parity.py --ticks 100 --peer
+
+--peer: halo rows and migrating agents cross as peer stores into CUDA-IPC mailboxes, the whole tick is one
+pf_strip_tick call (the product path); --legacy keeps the round-1 host loop with NCCL migration.
+--same-device: every rank uses cuda:0 and gloo carries the set-up (NCCL refuses two ranks on one GPU) — the
+cross-process mailbox protocol on a box with a single GPU (tests/test_gpu_multiproc.py).
 """
 import argparse
 import os
@@ -25,12 +30,18 @@ ap.add_argument("--no-overlap", action="store_true")
 ap.add_argument("--sort-every", type=int, default=16)
 ap.add_argument("--no-hand-over", action="store_true")
 ap.add_argument("--peer", action="store_true", help="peer-store halo (CUDA IPC + NVLink P2P) instead of NCCL")
+ap.add_argument("--legacy", action="store_true", help="phase-by-phase host loop with NCCL migration (round 1)")
+ap.add_argument("--same-device", action="store_true", help="all ranks on cuda:0, gloo for the set-up")
 args = ap.parse_args()
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-local = int(os.environ.get("LOCAL_RANK", rank))
+local = 0 if args.same_device else int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if args.same_device:
+    assert args.peer and not args.legacy, "--same-device needs the mailbox path (--peer, no --legacy)"
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 H = W = args.grid
 cfg = abi.default_config(H, W, 2)
@@ -54,7 +65,9 @@ p = parts[rank]
 scfg = sharded.strip_config(cfg, world, rank, device=local)
 strip = sharded.CudaStrip(scfg, p["x"], p["y"], p["theta"], p["state"], p["gid"],
                           capacity=int(len(p["x"]) * 1.5) + 1024, migrate_cap=8192)
-drv = sharded.DistDriver(sharded.StripWorker(strip, rank, world), overlap=not args.no_overlap)
+if args.same_device:
+    strip.field.set_option(abi.OPT_PEER_TIMEOUT_MS, 20000)  # the ranks time-slice one GPU: waits span context switches
+drv = sharded.DistDriver(sharded.StripWorker(strip, rank, world), overlap=not args.no_overlap, legacy=args.legacy)
 if args.peer:
     strip.peer_attach_ipc(rank, world)
     dist.barrier()
@@ -66,29 +79,22 @@ for t in range(args.ticks):
     # interior rows hand their next deposit to the stencil, except before a re-sort and on the last tick
     before_sort = args.sort_every and (t + 1) % args.sort_every == 0
     drv.tick(True, hand_over=not (before_sort or t == args.ticks - 1 or args.no_hand_over))
+    if args.same_device and t % 8 == 7:
+        strip.field.peer_status()  # stop early (raises) instead of piling up timeouts if the ranks cannot overlap
 torch.cuda.synchronize()
 
+strip.field.peer_status()  # raises if a bounded peer wait gave up
+
 # gather strips on rank 0
-field_local = torch.from_numpy(strip.field.snapshot()).cuda()
-sizes = [sharded.strip_bounds(H, world, r) for r in range(world)]
 sw = strip.swarm.to_numpy()
 alive = (sw["meta"] & 3) != 0
 rec = np.stack([sw[f][alive].view(np.uint32) for f in ("gid", "x", "y", "theta", "wl", "wr", "meta")], 1)
-counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-dist.all_gather(counts, torch.tensor([rec.shape[0]], dtype=torch.int64, device="cuda"))
+gathered = [None] * world if rank == 0 else None
+dist.gather_object((strip.field.snapshot(), rec), gathered, dst=0)
 ok = True
 if rank == 0:
-    fields = [field_local]
-    recs = [rec]
-    for r in range(1, world):
-        rows = sizes[r][1] - sizes[r][0]
-        buf = torch.empty((2, rows, W), dtype=torch.float32, device="cuda")
-        dist.recv(buf, r)
-        fields.append(buf)
-        rb = torch.empty((int(counts[r].item()), 7), dtype=torch.int32, device="cuda")
-        dist.recv(rb, r)
-        recs.append(rb.cpu().numpy().view(np.uint32))
-    field = torch.cat(fields, 1).cpu().numpy()
+    field = np.concatenate([g_[0] for g_ in gathered], axis=1)
+    recs = [g_[1] for g_ in gathered]
     allrec = np.concatenate(recs)
     allrec = allrec[np.argsort(allrec[:, 0], kind="stable")]
     # unsharded run on this GPU
@@ -98,6 +104,7 @@ if rank == 0:
     torch.cuda.synchronize()
     want_f = g.snapshot()
     w = s1.to_numpy()
+    g.close()
     same_field = bool((field.view(np.uint32) == want_f.view(np.uint32)).all())
     same_n = allrec.shape[0] == n
     same_agents = same_n and all(
@@ -106,12 +113,9 @@ if rank == 0:
     mig = strip.field.counters()
     ok = same_field and same_agents
     att, fb = strip.field.tile_stats()
-    print(f"dist_parity world={world} hand-over ticks on rank 0: {att} (fell back {fb}); peer_halo={args.peer} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
+    print(f"dist_parity world={world} hand-over ticks on rank 0: {att} (fell back {fb}); peer_halo={args.peer} path={'legacy host loop + NCCL migration' if (args.legacy or not args.peer) else 'pf_strip_tick + mailbox migration'} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
           f"agents_bitexact={same_agents} (rank0 migrated_out={mig.migrated_out}, dropped={mig.migrate_dropped}) "
           f"-> {'PASS' if ok else 'FAIL'}", flush=True)
-else:
-    dist.send(field_local, 0)
-    dist.send(torch.from_numpy(rec.view(np.int32)).cuda(), 0)
 dist.barrier()
 strip.field.close()
 dist.destroy_process_group()
