@@ -29,6 +29,15 @@ from pathlib import Path
 
 import numpy as np
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
@@ -188,6 +197,75 @@ def cpu_port_throughput(cfg_full, n_agents_full, budget_s=12.0, threads=None, st
     }, dt / max(1, ticks) * T
 
 
+def cpu_reference_legs(budget_s=9.0):
+    """the reference's own Python arithmetic, timed single-threaded on this box's host
+    (the reference has no parallelism). The reference checkout does not travel to the GPU box, so each leg is the
+    few lines it consists of, stated here with their file:line, on the reference's own sizes:
+      algo_literal   Phase-3/pheromone_algo.py:351-356 — deposit into one cell, then `grid[i][j] *= (1 - rate)` over
+                     every cell of a list of lists, at 10 x 10 (as shipped) and 1024 x 1024
+      graph_loop     Phase-3/graph.py:17-24 — `heatmap[..] += 20; heatmap = gaussian_filter(heatmap, 5)` per
+                     trajectory point on the 497 x 495 float64 map (scipy), points of Phase-3/heatmap.txt
+      sup_trail      Phase-3/pheromone_algo_supervisor.py:565-607 — one supervisor tick (deposit, sense, adjust,
+                     age-window evaporation) per recorded pose of the shipped trajectory, through oracle/trail.py
+                     (the f64 restatement that equals the real reference's traces exactly; kind "port")
+    """
+    out = {"cores": 1, "note": "single thread; reference figures measured on the real files in the build container: "
+                               "SURVEY.md §6 (8-21 M cell-updates/s, 850 agent-steps/s)"}
+    share = budget_s / 4.0
+
+    def algo_literal(N):
+        grid = [[0.0] * N for _ in range(N)]
+        intensity, rate = 1.0, 0.1
+        t0 = time.perf_counter()
+        k = 0
+        while True:
+            grid[3 % N][4 % N] += intensity               # algo:351
+            for i in range(N):                            # algo:354-356
+                row = grid[i]
+                for j in range(N):
+                    row[j] *= (1 - rate)
+            k += 1
+            if time.perf_counter() - t0 >= share or (N <= 16 and k >= 20000):
+                break
+        dt = time.perf_counter() - t0
+        return {"grid": N, "steps": k, "ms_per_step": dt / k * 1e3, "cell_updates_per_s": N * N * k / dt}
+
+    out["algo_literal_10"] = algo_literal(10)
+    out["algo_literal_1024"] = algo_literal(1024)
+    try:
+        from scipy.ndimage import gaussian_filter
+        g = json.loads((ROOT / "tests" / "golden" / "sup_replay_heatmap.json").read_text())
+        H, W = 497, 495                                   # background.png, graph.py:7-10
+        heat = np.zeros((H, W))
+        t0 = time.perf_counter()
+        k = 0
+        for p in g["positions"]:
+            r, c = abs(int(p[1] * H)), abs(int(p[0] * W))  # graph.py:19-22
+            heat[r, c] += 20                               # graph.py:23
+            heat = gaussian_filter(heat, sigma=5)          # graph.py:24
+            k += 1
+            if time.perf_counter() - t0 >= share:
+                break
+        dt = time.perf_counter() - t0
+        out["graph_loop_497x495"] = {"points": k, "ms_per_step": dt / k * 1e3, "cell_updates_per_s": H * W * k / dt,
+                                     "mass": float(heat.sum()), "mass_expected": 20.0 * k}
+        from oracle import trail
+        o = trail.TrailOracle(g["start"], g["food"], ps=(g["ps"],) * 8)
+        t0 = time.perf_counter()
+        k = 0
+        for rec, pos in zip(g["ticks"], g["positions"]):
+            o.tick(rec["t"], pos)
+            k += 1
+            if time.perf_counter() - t0 >= share:
+                break
+        dt = time.perf_counter() - t0
+        out["sup_trail_c0_replay"] = {"ticks": k, "ms_per_tick": dt / k * 1e3, "agent_steps_per_s": k / dt,
+                                      "kind": "port (oracle/trail.py, exact vs the reference's golden traces)"}
+    except Exception as e:  # a missing fixture must not cost the headline
+        out["error"] = repr(e)
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -207,7 +285,7 @@ def run_reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_dict(args, cfg, n):
@@ -221,6 +299,14 @@ def workload_dict(args, cfg, n):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def init_agents_torch(cfg, n, device, seed=1234):
+    """(x, y, theta, state) of the synthetic population (torch Philox on the host, fixed seed — used only for the
+    INITIAL poses; the reference has no random draws).
+    Uniform over the arena, all SEARCHING, for configs 1-3. Config 4 (fsm on): SURVEY §8d's nest cluster (nest +-
+    5 % of the arena width, SEARCHING) for 7/8 of the robots; the arena is 164 m wide and a robot covers 3.3 mm per
+    tick, so in a bench-length run nobody would get from the nest to a food source or back — the outcome counters
+    would stay at zero. The remaining 1/8 is therefore a slice of a run in progress: 1/16 SEARCHING within 2 m of
+    the eight food sources (those crossing a food disc grab), 1/16 HOMING carriers 4-70 cm from the nest (inside
+    the home radius: they steer by sup:489-500 and deliver in the 5-6 cm window, sup:665-670)."""
     import torch
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
@@ -228,10 +314,25 @@ def init_agents_torch(cfg, n, device, seed=1234):
     x = torch.rand(n, generator=g) * xmax
     y = torch.rand(n, generator=g) * ymax
     th = (torch.rand(n, generator=g) * 2 - 1) * float(np.pi)
-    if cfg.fsm:  # c4: start around the nest, +-5 % of the arena width
+    st = torch.full((n,), abi.STATE_SEARCHING, dtype=torch.int64)
+    if cfg.fsm:
         x = cfg.nest_x + (torch.rand(n, generator=g) * 2 - 1) * 0.05 * xmax
         y = cfg.nest_y + (torch.rand(n, generator=g) * 2 - 1) * 0.05 * ymax
-    return x.float().numpy(), y.float().numpy(), th.float().numpy()
+        k = n // 16
+        if k > 0:
+            r = 2.0 * torch.sqrt(torch.rand(k, generator=g))
+            a = torch.rand(k, generator=g) * 2 * float(np.pi)
+            src = torch.randint(0, cfg.n_food, (k,), generator=g)
+            fx = torch.tensor([cfg.food_x[i] for i in range(cfg.n_food)])
+            fy = torch.tensor([cfg.food_y[i] for i in range(cfg.n_food)])
+            x[:k] = fx[src] + r * torch.cos(a)
+            y[:k] = fy[src] + r * torch.sin(a)
+            r2 = 0.04 + 0.66 * torch.rand(k, generator=g)
+            a2 = torch.rand(k, generator=g) * 2 * float(np.pi)
+            x[k:2 * k] = cfg.nest_x + r2 * torch.cos(a2)
+            y[k:2 * k] = cfg.nest_y + r2 * torch.sin(a2)
+            st[k:2 * k] = abi.STATE_HOMING
+    return x.float().numpy(), y.float().numpy(), th.float().numpy(), st.numpy()
 
 
 def measure_other_config(name, steps, sort_every=16):
@@ -240,9 +341,9 @@ def measure_other_config(name, steps, sort_every=16):
 
     from swarm_robotics_pheromones_b200.field import PheroField, Swarm
     cfg, n = make_config(name)
-    x, y, th = init_agents_torch(cfg, n, "cuda")
+    x, y, th, st = init_agents_torch(cfg, n, "cuda")
     f = PheroField(cfg)
-    sw = Swarm(x, y, th)
+    sw = Swarm(x, y, th, st)
     f.reserve_agents(n)
     cells = cfg.H * cfg.W * cfg.C
     if cells <= (1 << 24):
@@ -319,12 +420,14 @@ def run_single(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(0)
     cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
-    x, y, th = init_agents_torch(cfg, n, "cuda")
+    x, y, th, st0 = init_agents_torch(cfg, n, "cuda")
     field = PheroField(cfg)
     field.set_stencil_variant(args.variant, args.rows_per_cta)
     if args.overlap_agents:
         field.set_option(abi.OPT_OVERLAP_AGENTS, 1)
-    swarm = Swarm(x, y, th)
+    if args.force_owner_deposit:
+        field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
+    swarm = Swarm(x, y, th, st0)
     field.reserve_agents(n)
     field.set_time(0.0, 0.0)
     cells = cfg.H * cfg.W * cfg.C
@@ -395,6 +498,8 @@ def run_single(args):
                 "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                 "frac_of_8TBs_nominal": ach / 8000.0,
                 "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                "traffic_source": (None if not tr else f"ncu --set full capture of this kernel, {tr.get('source', 'profiles/')}"
+                                                      f" (not measured in this run)"),
                 "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL_UPDATE,
                 "launch_ms": st_ms,
                 "phase_ms": {"deposit": prof.deposit_ms / max(1, prof.ticks), "stencil": st_ms,
@@ -452,6 +557,7 @@ def run_single(args):
     cb = None
     if not args.no_cpu:
         cb, _ = cpu_port_throughput(cfg, n, budget_s=args.cpu_seconds)
+        cb["reference_python_legs"] = cpu_reference_legs()
 
     line = {
         "metric": "grid cell-updates/s (agent-steps/s alongside)", "value": value,
@@ -464,7 +570,7 @@ def run_single(args):
         "agent_sorts_in_timed_region": sorts_timed,
         "other_configs": others, "sparse_trail_engine": trail_eng,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     field.close()
 
 
@@ -488,21 +594,29 @@ def run_sharded(args):
         os.environ["NCCL_DEBUG_FILE"] = nccl_log
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
-    scfg = sharded.strip_config(cfg, world, rank, device=local)
     # every rank draws the same global population and keeps its own strip's agents
-    x, y, th = init_agents_torch(cfg, n, "cuda")
+    x, y, th, st0 = init_agents_torch(cfg, n, "cuda")
     rows = sharded.agent_rows(cfg, x)
+    bounds = None
+    balance = args.balance == "on" or (args.balance == "auto" and cfg.fsm)
+    if balance:  # strips of equal cost instead of equal height: bytes per row = its cells + the robots on it
+        per_row = np.bincount(rows, minlength=cfg.H).astype(np.float64)
+        row_cost = cfg.W * cfg.C * BYTES_PER_CELL_UPDATE + per_row * 260.0   # 260 B: measured DRAM bytes per agent-step
+        bounds = sharded.weighted_bounds(row_cost, world, min_rows=256)
+    scfg = sharded.strip_config(cfg, world, rank, device=local, bounds=bounds)
     mine = np.nonzero((rows >= scfg.row0) & (rows < scfg.row1))[0]
     n_local = len(mine)
     cap = int(n_local * 1.25) + 4096
-    mcap = max(4096, int(4 * n / cfg.H) + 4096)
-    strip = sharded.CudaStrip(scfg, x[mine], y[mine], th[mine], np.full(n_local, abi.STATE_SEARCHING),
-                              mine.astype(np.uint32), cap, mcap)
+    per_row_max = float(np.bincount(rows, minlength=cfg.H).max())
+    mcap = max(4096, int(4 * per_row_max) + 4096)   # robots that can cross one strip edge in a tick, with slack
+    strip = sharded.CudaStrip(scfg, x[mine], y[mine], th[mine], st0[mine], mine.astype(np.uint32), cap, mcap)
+    if args.force_owner_deposit:
+        strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
     del x, y, th, rows
     strip.field.set_stencil_variant(args.variant, args.rows_per_cta)
     worker = sharded.StripWorker(strip, rank, world)
-    drv = sharded.DistDriver(worker, overlap=not args.no_overlap, profile=args.phase_profile,
-                             legacy=args.legacy_loop or args.nccl_halo)
+    legacy = args.legacy_loop or args.nccl_halo
+    drv = sharded.DistDriver(worker, overlap=not args.no_overlap, profile=args.phase_profile and legacy, legacy=legacy)
     if not args.nccl_halo:
         # halo exchange fused into the deposit / stencil kernels: edge rows are stored straight into
         # the neighbours' ghost rows over NVLink (CUDA IPC mappings); NCCL only carries migrants
@@ -529,14 +643,23 @@ def run_sharded(args):
     dist.barrier()
     tick_no[0] = 0  # the timed region pays ceil(K / sort_every) sorts
     sampler = ClockSampler(local)
+    if args.phase_profile and not legacy:
+        strip.field.profile(True)   # CUDA events at the phase boundaries inside pf_strip_tick
     l0 = strip.field.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     torch.cuda.synchronize()
+    tick_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] if args.tick_times else None
     e0.record()
+    h0 = time.perf_counter()
     for k in range(args.steps):
+        if tick_ev:
+            tick_ev[k].record()
         tick(last=k == args.steps - 1)
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3
     e1.record()
+    if tick_ev:
+        tick_ev[args.steps].record()
     torch.cuda.synchronize()
     dist.barrier()
     clocks = sampler.stop()
@@ -544,6 +667,10 @@ def run_sharded(args):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = strip.field.launch_count() - l0
+    mine_ph = None
+    if args.phase_profile and not legacy:
+        mine_ph = strip.field.strip_profile()
+        strip.field.profile(False)
     strip.field.peer_status()  # raises if a bounded peer wait gave up (a rank out of lockstep)
     c_run = strip.field.counters()
     lost = torch.tensor([float(c_run.migrate_dropped), float(c_run.migrated_out), float(c_run.migrated_in)],
@@ -608,11 +735,19 @@ def run_sharded(args):
     counts = torch.tensor([float(sw.alive().sum().item())], device="cuda", dtype=torch.float64)
     allc = [torch.zeros_like(counts) for _ in range(world)]
     dist.all_gather(allc, counts)
+    c_end = strip.field.counters()
+    food = torch.tensor([float(c_end.food_grabbed), float(c_end.food_delivered), float(c_end.deposits)],
+                        device="cuda", dtype=torch.float64)
+    dist.all_reduce(food)
+    rows_all = [None] * world
+    dist.all_gather_object(rows_all, [int(scfg.row0), int(scfg.row1)])
 
     phases_all = None
     if args.phase_profile:
         phases_all = [None] * world
-        dist.all_gather_object(phases_all, sharded.phase_means(drv))
+        if legacy:
+            mine_ph = sharded.phase_means(drv)
+        dist.all_gather_object(phases_all, mine_ph)
     if rank == 0:
         line = {
             "metric": "grid cell-updates/s (agent-steps/s alongside)",
@@ -633,18 +768,27 @@ def run_sharded(args):
                          "algorithmic_bytes_per_launch": local_cells * BYTES_PER_CELL_UPDATE},
             "cpu_baseline": None,
             "agents_per_rank": [int(c.item()) for c in allc],
+            "strip_rows_per_rank": rows_all, "strips": "equal cost (cells + robots per row)" if balance else "equal height",
             "agent_imbalance_max_over_mean": float(max(c.item() for c in allc) / max(1.0, np.mean([c.item() for c in allc]))),
             "migrated_agents_total": int(lost[1].item()), "migrate_dropped": int(lost[0].item()),
-            "tick_driver": ("host loop, NCCL migration (round-1 path)" if (args.legacy_loop or args.nccl_halo or args.phase_profile)
+            "tick_driver": ("host loop, NCCL migration (round-1 path)" if legacy
                             else "pf_strip_tick: one C call per tick, leavers through peer mailboxes"),
             "halo_overlap": not args.no_overlap, "stencil_variant": args.variant,
             "halo": "nccl send/recv" if args.nccl_halo else "peer stores fused into the kernels (CUDA IPC, NVLink P2P)",
             "agent_sort_every": args.sort_every,
+            "host_enqueue_ms_per_step_rank0": host_enqueue_ms / args.steps,
         }
+        if tick_ev:
+            line["tick_ms_rank0"] = [round(tick_ev[k].elapsed_time(tick_ev[k + 1]), 4) for k in range(args.steps)]
+        if cfg.fsm:  # the dissertation's outcome metric next to the throughput (PDF p.19-21; metrics.py)
+            from swarm_robotics_pheromones_b200.metrics import NetEnergy
+            line["foraging"] = {"food_grabbed": int(food[0].item()), "food_delivered": int(food[1].item()),
+                                "deposits": int(food[2].item()), "ticks": int(c_end.ticks),
+                                "net_energy": NetEnergy().update(int(food[1].item()), int(c_end.ticks), n)}
         if args.phase_profile:
             line["phase_ms_rank0"] = phases_all[0]
             line["phase_ms_all_ranks"] = phases_all
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier()
     strip.field.close()
     dist.destroy_process_group()
@@ -684,11 +828,23 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="sharded run: NCCL send/recv halo instead of peer stores")
     ap.add_argument("--phase-profile", action="store_true", help="sharded run: per-phase CUDA events")
+    ap.add_argument("--balance", default="auto", choices=["auto", "on", "off"],
+                    help="sharded run: strips of equal cost (cells + robots per row) instead of equal height; "
+                         "auto = for config 4's clustered population")
+    ap.add_argument("--force-owner-deposit", action="store_true",
+                    help="sort-free deposit even where the density heuristic prefers the global radix sort")
+    ap.add_argument("--tick-times", action="store_true", help="sharded run: device time of every timed tick (rank 0)")
     ap.add_argument("--legacy-loop", action="store_true",
                     help="sharded run: round-1 tick driver (phase-by-phase host loop, NCCL migration)")
     ap.add_argument("--no-hand-over", action="store_true",
                     help="sharded run: always use the separate deposit kernel (no deposits riding on the stencil)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, for one) is
+    # sent to stderr instead, and the line itself goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":

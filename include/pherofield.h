@@ -350,6 +350,12 @@ int pf_peer_status(pf_handle* h, void* stream);
 #define PF_TICK_ALL 0x7u
 int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, uint32_t phases, void* stream);
 
+/* Per-phase device times of pf_strip_tick while profiling is enabled (pf_profile_enable), summed over `ticks`:
+ * [0] deposit, [1] halo signal + stencil over the first rows, [2] halo wait + ghost rows, [3] sense/decide/move
+ * (+ hand-over bins and grouping), [4] pack + migration signal, [5] stencil over the remaining rows, [6] migration
+ * wait, [7] unpack, [8..10] unused. Synchronises the device. */
+int pf_strip_profile(pf_handle* h, double* ms_out11, uint64_t* ticks, int reset);
+
 /* pf_snapshot_host, pf_field_sum_host and pf_counters_host return PF_ESTATE between a hand-over tick and the next
  * deposit (the interior rows and the deposit counters are one tick ahead). */
 int pf_counters_host(pf_handle* h, pf_counters* out_host, void* stream);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pf_peer_wait": (C.c_int, [_vp, _vp]),
     "pf_peer_status": (C.c_int, [_vp, _vp]),
     "pf_strip_tick": (C.c_int, [_vp, _agp, C.c_uint32, C.c_uint32, _vp]),
+    "pf_strip_profile": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "pf_counters_host": (C.c_int, [_vp, C.POINTER(abi.PFCounters), _vp]),
     "pf_counters_reset": (C.c_int, [_vp, _vp]),
     "pf_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),

@@ -186,38 +186,72 @@ class ReferenceCompat:
         """One supervisor tick for every robot from HOST poses (pinned [3][N]: x, y, theta):
         H2D poses -> observe -> deposit -> sense/decide -> evaporate(+diffuse) -> D2H wheel speeds
         and decisions. The caller (Webots in the reference) owns the motion, so PF_STEP_MOVE is
-        not run. Returns (wl, wr, decision) host tensors (views of pinned staging)."""
+        not run. Returns (wl, wr, decision) host tensors (views of pinned staging) as soon as they have
+        arrived: the supervisor needs the speeds, not the field — the evaporate+diffuse kernel of this
+        tick may still be running and everything issued later is ordered behind it on the stream."""
         self.tick_host_async(pose_host)
-        torch.cuda.current_stream(self.field.device).synchronize()
+        self._ev_out.synchronize()
         return self._h_out[0], self._h_out[1], self._h_dec
 
+    CHUNKS = 4
+
+    def _chunk_views(self):
+        """robot sub-ranges as pf_agents views (pointer arithmetic only), for the pipelined host path"""
+        if getattr(self, "_chunks", None) is None:
+            n = self.swarm.n
+            k = self.CHUNKS if n >= (1 << 16) else 1
+            cuts = [(n * i // k) // 256 * 256 for i in range(k)] + [n]
+            self._chunks = [(a, b, _SwarmSlice(self.swarm, a, b - a)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        return self._chunks
+
     def tick_host_async(self, pose_host: torch.Tensor):
-        """Phases driven from the host so that the D2H of the wheel speeds (ready after the decide
-        kernel) overlaps the evaporate+diffuse kernel: main stream = H2D, observe, deposit, field;
-        side stream = decide, D2H."""
+        """The tick as a pipeline over robot sub-ranges (the copies dominate: 12 B in, 9 B out per robot):
+          copy-in stream   H2D of chunk i            | main: observe chunk i as soon as it has landed
+          main stream      deposit (all robots), then decide chunk i -> evaporate+diffuse
+          copy-out stream  D2H of chunk i's speeds and decisions beside decide chunk i+1 and the field kernel
+        Before the start delay observe is skipped: the reference only stores poses inside deposit_pheromone
+        (sup:279-289, 577), so the first deposit after t = 5 s is unconditional (old_pos is None, sup:261-262)."""
         f, sw = self.field, self.swarm
         main = torch.cuda.current_stream(f.device)
         if not hasattr(self, "_side"):
-            self._side = torch.cuda.Stream(f.device)
-            self._ev_dep = torch.cuda.Event()
-            self._ev_dec = torch.cuda.Event()
+            self._side = torch.cuda.Stream(f.device)       # copy-out
+            self._cin = torch.cuda.Stream(f.device)        # copy-in
+            self._ev_in = [torch.cuda.Event() for _ in range(self.CHUNKS)]
+            self._ev_dec = [torch.cuda.Event() for _ in range(self.CHUNKS)]
             self._ev_out = torch.cuda.Event()
+            self._ev_free = torch.cuda.Event()
+            self._ev_free.record(main)
         t, _ = f.time()
         sensing = t >= f.start_delay
-        self._d_pose.copy_(pose_host, non_blocking=True)
-        f.observe(sw, self._d_pose[0], self._d_pose[1], self._d_pose[2])
+        chunks = self._chunk_views()
+        self._cin.wait_event(self._ev_free)                # the previous tick's observe has consumed _d_pose
+        with torch.cuda.stream(self._cin):
+            for i, (a, b, _) in enumerate(chunks):
+                for r in range(3):  # row by row: contiguous 1-D copies (a strided 2-D one is staged by torch)
+                    self._d_pose[r, a:b].copy_(pose_host[r, a:b], non_blocking=True)
+                self._ev_in[i].record(self._cin)
+        for i, (a, b, view) in enumerate(chunks):
+            main.wait_event(self._ev_in[i])
+            if sensing:
+                f.observe(view, self._d_pose[0, a:], self._d_pose[1, a:], self._d_pose[2, a:])
+            else:                                          # poses only; no has_moved bookkeeping yet
+                sw.x[a:b].copy_(self._d_pose[0, a:b]); sw.y[a:b].copy_(self._d_pose[1, a:b])
+                sw.theta[a:b].copy_(self._d_pose[2, a:b])
+        self._ev_free.record(main)
         if sensing:
             f.agents_deposit(sw)
-        # decide on the main stream (two HBM-bound kernels side by side only slow each other down);
-        # the kernel writes the u8 decisions itself
-        f.agents_step(sw, abi.STEP_SENSE if sensing else 0, decisions=self._d_dec)
-        self._ev_dec.record(main)
-        with torch.cuda.stream(self._side):  # D2H rides beside the stencil
-            self._side.wait_event(self._ev_dec)
-            self._h_out[0].copy_(sw.wl, non_blocking=True)
-            self._h_out[1].copy_(sw.wr, non_blocking=True)
-            self._h_dec.copy_(self._d_dec, non_blocking=True)
-            self._ev_out.record(self._side)
+        self._side.wait_event(self._ev_out)                # (re-use of the staging: previous D2H done)
+        for i, (a, b, view) in enumerate(chunks):
+            # decide on the main stream (two HBM-bound kernels side by side only slow each other down);
+            # the kernel writes the u8 decisions itself
+            f.agents_step(view, abi.STEP_SENSE if sensing else 0, decisions=self._d_dec[a:])
+            self._ev_dec[i].record(main)
+            with torch.cuda.stream(self._side):            # D2H rides beside the next chunk and the stencil
+                self._side.wait_event(self._ev_dec[i])
+                self._h_out[0, a:b].copy_(sw.wl[a:b], non_blocking=True)
+                self._h_out[1, a:b].copy_(sw.wr[a:b], non_blocking=True)
+                self._h_dec[a:b].copy_(self._d_dec[a:b], non_blocking=True)
+        self._ev_out.record(self._side)
         f.step(sw, 1, abi.STEP_FIELD)  # evaporate+diffuse only; advances the tick clock
         main.wait_event(self._ev_out)
 
@@ -243,11 +277,11 @@ class _NameIndex:
 
 
 class _SwarmSlice:
-    """pf_agents view of a single slot of a Swarm (pointer arithmetic only)."""
+    """pf_agents view of `n` slots of a Swarm starting at slot i (pointer arithmetic only)."""
 
-    def __init__(self, sw: Swarm, i: int):
+    def __init__(self, sw: Swarm, i: int, n: int = 1):
         s = abi.PFAgents()
-        s.n = 1
+        s.n = n
         s.x, s.y, s.theta = sw.x[i:].data_ptr(), sw.y[i:].data_ptr(), sw.theta[i:].data_ptr()
         s.wl, s.wr = sw.wl[i:].data_ptr(), sw.wr[i:].data_ptr()
         s.meta, s.gid = sw.meta[i:].data_ptr(), sw.gid[i:].data_ptr()

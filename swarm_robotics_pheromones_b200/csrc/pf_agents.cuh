@@ -392,9 +392,9 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
         // next_keys: every agent's key is written. tb.bcnt: agents whose cell lies in a tile the
         // stencil takes care of are handed over through the tile's bin (pf_deposit_tile.cuh); on a
         // strip (no next_keys) the others are left to the next tick's key kernel, untouched.
-        uint32_t key = sentinel, local = 0u;
+        uint32_t key = sentinel, local = 0u, code = 0u;
         float amt = 0.0f;
-        int tile = -1;
+        int tile = -1;  // bin of the stencil tile and stage group that writes the agent's cell
         if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && moved) {
           int r, q;
           const bool inside = pf_cell(p, x, y, r, q);
@@ -402,8 +402,8 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
           if (mine && tb.bcnt) tile = tile_of(tb, p.dep_ch[st], r - p.row0, q, &local);
           if (next_keys || tile >= 0) {
             uint32_t cnt = ((nm >> PF_META_COUNT_SHIFT) + 1u) & PF_META_COUNT_MASK;
-            amt = (st == PF_STATE_SEARCHING) ? ((cnt % p.high_every == 0u) ? p.i_high : p.i_explore)
-                                             : p.i_homing;
+            code = (st == PF_STATE_SEARCHING) ? ((cnt % p.high_every == 0u) ? 1u : 0u) : 2u;
+            amt = code == 0u ? p.i_explore : (code == 1u ? p.i_high : p.i_homing);
             nm = (nm & 0xFFu) | (cnt << PF_META_COUNT_SHIFT);
             if (!next_keys) nm |= PF_META_HANDED;  // strips: the next key kernel skips this robot (or deposits it after all)
             if (mine) key = (uint32_t)(((long long)p.dep_ch[st] * p.rows + (r - p.row0)) * p.W + q);
@@ -418,7 +418,7 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
             owner_note_bounds(cmin, cmax, i / kOwnChunk, key % plane, key != sentinel);
           }
         }
-        if (tb.bcnt) tile_bin_put(tb, __activemask(), tile, local, amt, (uint32_t)i);
+        if (tb.bcnt) tile_bin_put(tb, __activemask(), tile, tile_record(local, code));
       }
       ameta[i] = nm;
       if (dec_out) dec_out[i] = (uint8_t)dec;

@@ -28,6 +28,8 @@ struct PFDev {
   // deposit
   float i_explore, i_high, i_homing;
   int dep_red;  // all intensities >= 1e-30: "cell += sum" may be a reduction at L2 (see pf_deposit_owner.cuh)
+  int dep_exact;  // all intensities are integers in [1, 32768]: a cell's total is exact whatever the order of the
+                  // additions, so the deposits riding on the stencil need no grouping pass (pf_deposit_tile.cuh)
   unsigned high_every;
   float move_thr;
   int dep_ch[4], sen_ch[4];

@@ -61,9 +61,7 @@ struct pf_handle {
   // owner-computes deposit (pf_deposit_owner.cuh): valid after pf_agents_sort for these arrays
   uint32_t *own_split, *own_cmin, *own_cmax, *own_pmax, *own_smin, *own_body, *own_tail;
   // deposit fused into the stencil (pf_deposit_tile.cuh): per-tile bins, per-tile lists, status flag
-  uint32_t *tile_bcnt, *tile_bkey, *tile_bidx, *tile_flag, *tile_count;
-  float* tile_bval;
-  unsigned char* tile_blk;
+  uint32_t *tile_bcnt, *tile_brec, *tile_flag;
   long long tile_alloc;   // tiles allocated
   int no_tile_deposit;
   bool tile_pending;      // lists are ready for (pf_step: were given to) the stencil launch over tile_ty0..ty1
@@ -90,6 +88,11 @@ struct pf_handle {
   unsigned long long peer_timeout_ns;
   int strip_dep0, strip_dep1;  // pf_strip_tick: rows handed over this tick (phase A decides, B and C use)
   bool strip_active;
+  // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
+  cudaEvent_t* strip_ev;
+  int strip_used, strip_mark;
+  double strip_ms[16];
+  unsigned long long strip_ticks;
   long long mig_flags_n;   // > 0: mig_cnt holds the per-chunk leaver counts the last move kernel made
   const float* mig_flags_x;
   uint32_t *mig_cnt, *mig_base, *emp_cnt, *emp_base;  // per chunk (two-level migration, pf_agents.cuh)
@@ -106,6 +109,7 @@ struct pf_handle {
 };
 
 constexpr int kProfSlots = 256;
+constexpr int kStripSlots = 64, kStripMarks = 12;
 
 static int set_err(pf_handle* h, int code, const char* fmt, ...) {
   char* dst = h ? h->err : g_create_err;
@@ -134,6 +138,7 @@ static int set_err(pf_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 static bool is_sharded(const pf_handle* h) { return h->cfg.row0 > 0 || h->cfg.row1 < h->cfg.H; }
+static int strip_fold(pf_handle* h);
 static long long mig_cap_of(const pf_config* c) { return c->migrate_cap > 0 ? c->migrate_cap : 16384; }
 // byte offset of the migration mailbox inside the peer block: behind the flag words and the halo rows
 static size_t mig_offset(int C, long long pitch) {
@@ -143,8 +148,7 @@ static size_t mig_box_words(long long cap) { return (size_t)(cap + 1) * PF_MIGRA
 static void graph_drop(pf_handle* h);
 
 static void tile_free(pf_handle* h) {
-  void** arrs[7] = {(void**)&h->tile_bcnt, (void**)&h->tile_bkey, (void**)&h->tile_bidx, (void**)&h->tile_flag,
-                    (void**)&h->tile_count, (void**)&h->tile_bval, (void**)&h->tile_blk};
+  void** arrs[3] = {(void**)&h->tile_bcnt, (void**)&h->tile_brec, (void**)&h->tile_flag};
   for (auto pp : arrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   h->tile_alloc = 0;
 }
@@ -265,6 +269,12 @@ static void derive(pf_handle* h) {
   d.del_thr = c.delete_threshold;
   d.i_explore = c.intensity_explore; d.i_high = c.intensity_high; d.i_homing = c.intensity_homing;
   d.dep_red = (c.intensity_explore >= 1e-30f && c.intensity_high >= 1e-30f && c.intensity_homing >= 1e-30f) ? 1 : 0;
+  {  // the reference's amounts are small integers (1, 20, 5): per-cell totals are then exact in any order
+    const float v[3] = {c.intensity_explore, c.intensity_high, c.intensity_homing};
+    d.dep_exact = 1;
+    for (float x : v)
+      if (!(x >= 1.0f && x <= 32768.0f && x == (float)(int)x)) d.dep_exact = 0;
+  }
   d.high_every = (unsigned)c.high_every;
   d.move_thr = c.move_threshold;
   for (int s = 0; s < 4; ++s) { d.dep_ch[s] = c.deposit_channel[s]; d.sen_ch[s] = c.sense_channel[s]; }
@@ -397,6 +407,10 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->prof_ev) {
     for (int i = 0; i < kProfSlots * 6; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;
+  }
+  if (h->strip_ev) {
+    for (int i = 0; i < kStripSlots * kStripMarks; ++i) cudaEventDestroy(h->strip_ev[i]);
+    delete[] h->strip_ev;
   }
   delete h;
   return PF_OK;
@@ -576,9 +590,11 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, 
   for (int k = 0; k < PF_MAX_CHANNELS; ++k) { a.keep[k] = d.keep[k]; a.dk[k] = d.dk[k]; }
   a.del_thr = d.del_thr;
   a.peer = peer_rows(h, h->cur ^ 1);
-  a.dep_flag = nullptr; a.dep_count = nullptr; a.dep_blk = nullptr; a.dep_ty0 = 0; a.dep_ny = 0;
+  a.dep_flag = nullptr; a.dep_cnt = nullptr; a.dep_rec = nullptr; a.dep_ty0 = 0; a.dep_ny = 0;
+  a.dep_amt[0] = a.dep_amt[1] = a.dep_amt[2] = 0.0f;
   if (with_deposits) {  // tile_ok() / strip_tile_range() hold: whole tile rows, TMA ring, CTA = deposit tile
-    a.dep_flag = h->tile_flag; a.dep_count = h->tile_count; a.dep_blk = h->tile_blk;
+    a.dep_flag = h->tile_flag; a.dep_cnt = h->tile_bcnt; a.dep_rec = h->tile_brec;
+    a.dep_amt[0] = d.i_explore; a.dep_amt[1] = d.i_high; a.dep_amt[2] = d.i_homing;
     int rc = tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, h->tile_ty1, s);
     if (rc != PF_OK) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
     h->launches++;
@@ -712,10 +728,10 @@ extern "C" int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_b
 // whole field, and no second stream.
 static bool tile_common_ok(const pf_handle* h, const pf_agents* a) {
   const PFDev& d = h->dev;
-  return !h->no_tile_deposit && !h->overlap_agents && owner_ready(h, a) && d.stencil != 0 && d.dep_red &&
+  return !h->no_tile_deposit && !h->overlap_agents && owner_ready(h, a) && d.stencil != 0 && d.dep_red && d.dep_exact &&
          d.W % 4 == 0 && d.W >= 512 && (h->variant == 0 || h->variant == 2) && h->rows_per_cta <= 0 &&
-         kTileRows == kDepRows && kTileEnt == kDepEnt && kTileCols == kTmaCols && kTileBlkBytes == kDepBlkBytes &&
-         kTilePtrBytes == kDepPtrBytes;
+         kTileRows == kDepRows && kTileCols == kTmaCols && kTileGroups == kDepGroups && kTileGroupCap == kDepCap &&
+         kTileHash == kDepHash && kTileNoRec == kDepNone;
 }
 static bool tile_ok(const pf_handle* h, const pf_agents* a) { return !is_sharded(h) && tile_common_ok(h, a); }
 
@@ -756,32 +772,25 @@ static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb, int ty0, int t
   const long long ntiles = (long long)nx * ny * h->dev.C;
   if (h->tile_alloc < ntiles) {
     tile_free(h);
-    PF_CUDA(h, cudaMalloc(&h->tile_bcnt, sizeof(uint32_t) * ntiles));
-    PF_CUDA(h, cudaMemset(h->tile_bcnt, 0, sizeof(uint32_t) * ntiles));
-    PF_CUDA(h, cudaMalloc(&h->tile_count, sizeof(uint32_t) * ntiles));
+    PF_CUDA(h, cudaMalloc(&h->tile_bcnt, sizeof(uint32_t) * ntiles * kTileGroups));
+    PF_CUDA(h, cudaMemset(h->tile_bcnt, 0, sizeof(uint32_t) * ntiles * kTileGroups));
     PF_CUDA(h, cudaMalloc(&h->tile_flag, 2 * sizeof(uint32_t)));  // [0] status of this tick, [1] fallbacks so far
     PF_CUDA(h, cudaMemset(h->tile_flag, 0, 2 * sizeof(uint32_t)));
-    PF_CUDA(h, cudaMalloc(&h->tile_bkey, sizeof(uint32_t) * ntiles * kOwnCap));
-    PF_CUDA(h, cudaMalloc(&h->tile_bval, sizeof(float) * ntiles * kOwnCap));
-    PF_CUDA(h, cudaMalloc(&h->tile_bidx, sizeof(uint32_t) * ntiles * kOwnCap));
-    PF_CUDA(h, cudaMalloc(&h->tile_blk, (size_t)ntiles * kTileBlkBytes));
+    PF_CUDA(h, cudaMalloc(&h->tile_brec, sizeof(uint32_t) * ntiles * kTileGroups * kTileGroupCap));
     h->tile_alloc = ntiles;
   }
   PF_CUDA(h, cudaMemsetAsync(h->tile_flag, 0, sizeof(uint32_t), s));
-  tb->bcnt = h->tile_bcnt; tb->bkey = h->tile_bkey; tb->bval = h->tile_bval; tb->bidx = h->tile_bidx;
+  tb->bcnt = h->tile_bcnt; tb->brec = h->tile_brec;
   tb->flag = h->tile_flag; tb->nx = nx; tb->ny = ny; tb->ty_lo = ty0; tb->ty_hi = ty1;
   h->tile_ty0 = ty0;
   h->tile_ty1 = ty1;
   return PF_OK;
 }
 
-// after the move kernel: bins -> per-tile lists for the stencil
+// after the move kernel: nothing to do — the stencil's deposit lanes read the bins themselves (round 1 grouped
+// them into per-tile lists here, 0.36 ms per tick at config 3)
 static int tile_finish(pf_handle* h, cudaStream_t s) {
-  const int nx = (h->dev.W + kTileCols - 1) / kTileCols, ny = (h->dev.rows + kTileRows - 1) / kTileRows;
-  const long long ntiles = (long long)nx * ny * h->dev.C;
-  k_tile_group<<<(unsigned)ntiles, kOwnThreads, 0, s>>>(h->tile_bcnt, h->tile_bkey, h->tile_bval, h->tile_bidx,
-                                                        h->tile_flag, h->tile_count, h->tile_blk);
-  PF_LAUNCH_CHECK(h);
+  (void)h; (void)s;
   return PF_OK;
 }
 
@@ -999,7 +1008,7 @@ extern "C" int pf_profile_enable(pf_handle* h, int on) {
     if (!h->prof_ev) return set_err(h, PF_ENOMEM, "host allocation failed");
     for (int i = 0; i < kProfSlots * 6; ++i) PF_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
   }
-  if (!on) { int rc = prof_fold(h); if (rc) return rc; }
+  if (!on) { int rc = prof_fold(h); if (rc) return rc; rc = strip_fold(h); if (rc) return rc; }
   h->prof_on = on ? 1 : 0;
   return PF_OK;
 }
@@ -1490,13 +1499,44 @@ static int strip_pack(pf_handle* h, const pf_agents* a, cudaStream_t s) {
 
 static int strip_unpack(pf_handle* h, const pf_agents* a, cudaStream_t s) {
   if (!h->peer_up.set && !h->peer_dn.set) return PF_OK;
-  k_peer_wait<<<1, 1, 0, s>>>(h->peer_up.set ? h->peer_flags + 2 : nullptr, h->peer_dn.set ? h->peer_flags + 3 : nullptr,
-                              h->mig_epoch, h->peer_timeout_ns, h->counters);
-  PF_LAUNCH_CHECK(h);
   uint32_t* from_up = h->peer_up.set ? mig_box_of(h->peer_flags, 0, h->cfg.C, h->dev.pitch, h->mig_cap) : nullptr;
   uint32_t* from_dn = h->peer_dn.set ? mig_box_of(h->peer_flags, 1, h->cfg.C, h->dev.pitch, h->mig_cap) : nullptr;
   return pf_migrate_unpack2(h, a, from_up, from_dn, h->mig_cap, (void*)s);
 }
+
+// fold the recorded marks of pf_strip_tick into per-phase sums (synchronises the device)
+static int strip_fold(pf_handle* h) {
+  if (!h->strip_used) return PF_OK;
+  PF_CUDA(h, cudaDeviceSynchronize());
+  for (int i = 0; i < h->strip_used; ++i) {
+    cudaEvent_t* e = h->strip_ev + (size_t)i * kStripMarks;
+    for (int k = 0; k + 1 < kStripMarks; ++k) {
+      float ms = 0.f;
+      PF_CUDA(h, cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+      h->strip_ms[k] += ms;
+    }
+    h->strip_ticks++;
+  }
+  h->strip_used = 0;
+  return PF_OK;
+}
+
+extern "C" int pf_strip_profile(pf_handle* h, double* ms_out11, uint64_t* ticks, int reset) {
+  if (!h || !ms_out11) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  int rc = strip_fold(h);
+  if (rc) return rc;
+  for (int k = 0; k < kStripMarks - 1; ++k) ms_out11[k] = h->strip_ms[k];
+  if (ticks) *ticks = h->strip_ticks;
+  if (reset) { memset(h->strip_ms, 0, sizeof(h->strip_ms)); h->strip_ticks = 0; }
+  return PF_OK;
+}
+
+#define STRIP_MARK()                                                                                  \
+  do {                                                                                                \
+    if (h->prof_on && h->strip_ev && h->strip_mark < kStripMarks)                                     \
+      PF_CUDA(h, cudaEventRecord(h->strip_ev[(size_t)h->strip_used * kStripMarks + h->strip_mark++], s)); \
+  } while (0)
 
 extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, uint32_t phases, void* stream) {
   int rc = check_agents(h, a);
@@ -1509,6 +1549,16 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
   if (a->n > 0) { rc = pf_reserve_agents(h, a->n); if (rc) return rc; }
   if (phases & PF_TICK_A) {  // deposit, halo signal
     if (h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase A twice (phases must run A, B, C)");
+    if (h->prof_on) {
+      if (!h->strip_ev) {
+        h->strip_ev = new (std::nothrow) cudaEvent_t[kStripSlots * kStripMarks];
+        if (!h->strip_ev) return set_err(h, PF_ENOMEM, "host allocation failed");
+        for (int i = 0; i < kStripSlots * kStripMarks; ++i) PF_CUDA(h, cudaEventCreate(&h->strip_ev[i]));
+      }
+      if (h->strip_used == kStripSlots) { rc = strip_fold(h); if (rc) return rc; }
+      h->strip_mark = 0;
+    }
+    STRIP_MARK();  // 0: start
     h->strip_dep0 = h->strip_dep1 = 0;
     if ((flags & PF_STEP_HANDOVER) && dep && move && (flags & PF_STEP_SENSE) && a->n > 0) {
       int ty0, ty1;
@@ -1518,6 +1568,7 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       }
     }
     if (dep && a->n > 0) { rc = pf_agents_deposit(h, a, stream); if (rc) return rc; }
+    STRIP_MARK();  // 1: deposit
     rc = pf_peer_signal(h, stream);
     if (rc) return rc;
     h->strip_active = true;
@@ -1528,15 +1579,19 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
   if (phases & PF_TICK_B) {  // interior rows while the halo is in flight, halo wait, agents, leavers out
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase B without phase A");
     if (mid > lo) { rc = launch_stencil(h, lo, mid, s); if (rc) return rc; }
+    STRIP_MARK();  // 2: signal + stencil over the first rows
     rc = pf_peer_wait(h, stream);
     if (rc) return rc;
+    STRIP_MARK();  // 3: halo wait + ghost rows
     if (a->n > 0 && (flags & (PF_STEP_SENSE | PF_STEP_MOVE))) {
       const uint32_t f = (flags & (PF_STEP_SENSE | PF_STEP_MOVE)) | (handing ? PF_STEP_HANDOVER : 0u);
       rc = pf_agents_step(h, a, f, nullptr, stream);
       if (rc) return rc;
       if (handing && !h->tile_pending) return set_err(h, PF_ESTATE, "pf_strip_tick: hand-over range changed inside a tick");
     }
+    STRIP_MARK();  // 4: sense/decide/move (+ bins + grouping)
     if (move) { rc = strip_pack(h, a, s); if (rc) return rc; }
+    STRIP_MARK();  // 5: pack + migration signal
   }
   if (phases & PF_TICK_C) {  // the remaining rows (deposits riding along), swap, arrivals in
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase C without phase A");
@@ -1555,9 +1610,21 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     if (rows > 1 && !last_done) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
     rc = pf_swap(h);
     if (rc) return rc;
+    STRIP_MARK();  // 6: stencil over the remaining rows
+    if (move && (h->peer_up.set || h->peer_dn.set)) {
+      k_peer_wait<<<1, 1, 0, s>>>(h->peer_up.set ? h->peer_flags + 2 : nullptr, h->peer_dn.set ? h->peer_flags + 3 : nullptr,
+                                  h->mig_epoch, h->peer_timeout_ns, h->counters);
+      PF_LAUNCH_CHECK(h);
+    }
+    STRIP_MARK();  // 7: migration wait
     if (move) { rc = strip_unpack(h, a, s); if (rc) return rc; }
     k_tick_counter<<<1, 1, 0, s>>>(h->counters);
     PF_LAUNCH_CHECK(h);
+    STRIP_MARK();  // 8: unpack
+    if (h->prof_on && h->strip_ev) {
+      while (h->strip_mark < kStripMarks) STRIP_MARK();  // unused marks: zero-length intervals
+      h->strip_used++;
+    }
     h->strip_active = false;
     h->strip_dep0 = h->strip_dep1 = 0;
   }

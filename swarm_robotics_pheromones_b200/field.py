@@ -288,6 +288,17 @@ class PheroField:
         """one whole strip tick by one C call (pf_strip_tick): leavers travel through the peer mailboxes"""
         self._ck(self._L.pf_strip_tick(self._h, C.byref(a.struct()), flags, phases, self._s()))
 
+    STRIP_PHASES = ("deposit", "signal+stencil_a", "wait_halo", "agents", "pack", "stencil_rest", "wait_migration",
+                    "unpack")
+
+    def strip_profile(self, reset: bool = True) -> dict:
+        """mean milliseconds per phase of pf_strip_tick over the ticks run since profile(True)"""
+        ms = (C.c_double * 11)()
+        n = C.c_uint64()
+        self._ck(self._L.pf_strip_profile(self._h, ms, C.byref(n), 1 if reset else 0))
+        k = max(1, n.value)
+        return {name: ms[i] / k for i, name in enumerate(self.STRIP_PHASES)} | {"ticks": n.value}
+
     # -- counters / tuning
     def counters(self) -> abi.PFCounters:
         c = abi.PFCounters()

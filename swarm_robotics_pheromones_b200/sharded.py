@@ -32,9 +32,29 @@ def strip_bounds(H: int, world: int, rank: int):
     return r0, r0 + base + (1 if rank < extra else 0)
 
 
-def strip_config(cfg: abi.PFConfig, world: int, rank: int, device: Optional[int] = None) -> abi.PFConfig:
+def weighted_bounds(row_cost: np.ndarray, world: int, min_rows: int = 128):
+    """strip boundaries [b0 = 0, b1, ..., b_world = H] that give every strip about the same total of `row_cost`
+    (bytes a tick moves for that row: its cells plus the robots standing on it) — for populations that crowd a
+    few rows, like config 4's nest. Every strip keeps at least `min_rows` rows."""
+    cost = np.asarray(row_cost, np.float64)
+    H = len(cost)
+    assert world * min_rows <= H
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    b = [0]
+    for r in range(1, world):
+        want = cum[-1] * r / world
+        k = int(np.searchsorted(cum, want))
+        k = max(k, b[-1] + min_rows)
+        k = min(k, H - (world - r) * min_rows)
+        b.append(k)
+    b.append(H)
+    return b
+
+
+def strip_config(cfg: abi.PFConfig, world: int, rank: int, device: Optional[int] = None,
+                 bounds: Optional[Sequence[int]] = None) -> abi.PFConfig:
     c = cfg.copy()
-    c.row0, c.row1 = strip_bounds(cfg.H, world, rank)
+    c.row0, c.row1 = (bounds[rank], bounds[rank + 1]) if bounds is not None else strip_bounds(cfg.H, world, rank)
     if device is not None:
         c.device = device
     return c
