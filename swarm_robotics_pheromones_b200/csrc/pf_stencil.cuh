@@ -29,10 +29,9 @@ struct StencilArgs {
   float del_thr;
   PeerRows peer;  // neighbour ghost rows of the NEXT buffer (null when not attached)
   // next tick's deposits, applied to the output rows (pf_deposit_tile.cuh; TMA variant only)
-  const uint32_t* dep_flag;   // != 0: the bins are not usable this tick (one overflowed)
-  uint32_t* dep_cnt;          // [tile * groups + g] records in the bin; read and reset by the tile's CTA
-  const uint32_t* dep_rec;    // [(tile * groups + g) * cap + k] records (pf_deposit_tile.cuh)
-  float dep_amt[3];           // the three amounts a record can name: explore, high, homing (sup:232-234)
+  const uint32_t* dep_flag;   // != 0: lists are not usable this tick
+  const uint32_t* dep_count;  // [tile] entries
+  const unsigned char* dep_blk;  // [tile] start[] / col[] / sum[] block
   int dep_ty0, dep_ny;           // tile row of this launch's first CTA row; tile rows per channel
 };
 

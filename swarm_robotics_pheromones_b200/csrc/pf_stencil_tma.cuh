@@ -16,14 +16,11 @@ constexpr int kTmaCols = kTmaWarps * 128;     // columns per CTA
 constexpr int kTmaRowFloats = kTmaCols + 8;   // + 4 halo floats each side
 constexpr int kTmaThreads = kTmaWarps * 32 + 32;  // + producer warp
 
-// deposits riding along (pf_deposit_tile.cuh; the constants are repeated here and compared on the host)
-constexpr int kDepRows = 64;     // rows per CTA (= kTileRows)
-constexpr int kDepGroups = 17;   // stage groups per tile (= kTileGroups)
-constexpr int kDepCap = 160;     // records per bin (= kTileGroupCap)
-constexpr int kDepHash = 256;    // hash slots (= kTileHash)
-constexpr int kDepPerLane = (kDepCap + 30) / 31;  // records a deposit lane holds of one bin
-constexpr int kDepSmemBytes = kDepHash * 8;       // keys[] + sums[]
-constexpr uint32_t kDepNone = 0xffffffffu;
+constexpr int kDepRows = 64;    // rows per CTA when deposits ride along (= kTileRows)
+constexpr int kDepEnt = 1408;   // = kTileEnt
+constexpr int kDepPtrBytes = 48;           // uint16 start[] of the per-stage entry groups (= kTilePtrBytes)
+constexpr int kDepColBytes = kDepEnt * 2;  // uint16 row << 10 | column
+constexpr int kDepBlkBytes = kDepPtrBytes + kDepColBytes + kDepEnt * 4;
 
 struct TmaStencilState {
   bool attr_set[3][9];
@@ -86,8 +83,9 @@ k_stencil_tma(StencilArgs a) {
   // 16 B aligned: ring rows are 4128 B, 2 * kStages + 3 slots of 8 B
   unsigned char* dblk =
       smem_raw + (((size_t)kStages * kStageRows * kTmaRowFloats * 4 + (2 * kStages + 3) * 8 + 15) & ~(size_t)15);
-  uint32_t* hkey = reinterpret_cast<uint32_t*>(dblk);  // hash of the deposit lanes: cell within the tile ...
-  float* hsum = reinterpret_cast<float*>(dblk + kDepHash * 4);  // ... and the total deposited there
+  const uint16_t* dstart = reinterpret_cast<const uint16_t*>(dblk);
+  const uint16_t* dcol = reinterpret_cast<const uint16_t*>(dblk + kDepPtrBytes);
+  const float* dsum = reinterpret_cast<const float*>(dblk + kDepPtrBytes + kDepColBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.z;
@@ -104,14 +102,19 @@ k_stencil_tma(StencilArgs a) {
   const uint32_t row_bytes = (uint32_t)(g1 - g0) * 4u;
   const int dst_off = g0 - (c0 - 4);
 
+  uint32_t ndep = 0u;
   long long tile = 0;
-  if (DEP) tile = ((long long)ch * a.dep_ny + a.dep_ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (DEP) {
+    tile = ((long long)ch * a.dep_ny + a.dep_ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (*a.dep_flag == 0u) ndep = a.dep_count[tile];  // uniform per CTA
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kTmaWarps);
     }
     if (DEP) {
+      mbar_init(dep_bar, 1);
       mbar_init(fin, kTmaWarps);
       *progress = 0u;
     }
@@ -127,14 +130,14 @@ k_stencil_tma(StencilArgs a) {
     // issued: once the consumers have released stage it - kStages (the producer's wait), every one of
     // them has issued its stores for the output rows of stage it - kStages - 1 (program order before
     // its arrive; arrive = release, wait = acquire), so a reduction sent to those cells now lands
-    // on the stored value, in L2, microseconds after the store: nxt[cell] = stencil value + total.
+    // on the stored value, in L2, microseconds after the store: nxt[cell] = stencil value + sum.
     float* const otile = a.nxt + ch * a.chan_stride + a.pitch + (long long)r0 * a.pitch + c0;
     if (lane == 0) {
       for (int it = 0; it < niter; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (uint32_t)(it / kStages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
-        if (DEP)  // a counter, not the barrier's parity: the deposit lanes may lag by any amount
+        if (DEP && ndep)  // a counter, not the barrier's parity: the deposit lanes may lag by any amount
           asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(progress)), "r"((uint32_t)it) : "memory");
         const int first = it * kStageRows;
         const int cnt = min(kStageRows, nstream - first);
@@ -145,62 +148,24 @@ k_stencil_tma(StencilArgs a) {
           bulk_g2s(ring + ((size_t)s * kStageRows + k) * kTmaRowFloats + dst_off,
                    base + (long long)r * a.pitch + g0, row_bytes, &full[s]);
         }
+        if (DEP && it == 0 && ndep) {  // the tile's deposit list, behind the first stage
+          const uint32_t col_bytes = (ndep * 2u + 15u) & ~15u, sum_bytes = (ndep * 4u + 15u) & ~15u;
+          const unsigned char* src = a.dep_blk + tile * kDepBlkBytes;
+          mbar_expect_tx(dep_bar, (uint32_t)kDepPtrBytes + col_bytes + sum_bytes);
+          bulk_g2s(dblk, src, (uint32_t)kDepPtrBytes + col_bytes, dep_bar);  // start[] and cell[] are adjacent
+          bulk_g2s(dblk + kDepPtrBytes + kDepColBytes, src + kDepPtrBytes + kDepColBytes, sum_bytes, dep_bar);
+        }
       }
-    } else if (DEP) {
-      // lanes 1..31 (diverged from the producer lane for good; they only meet it through `progress` and `fin`)
-      constexpr unsigned kLanes = 0xfffffffeu;
-      const int dl = lane - 1;
-      // this tile's bin fill counts: deposit lane g holds stage group g's and resets it for the next tick
-      // (also on a tick whose bins are not used: the next move kernel starts from zero either way)
-      uint32_t mycnt = 0u;
-      if (dl < kDepGroups) {
-        mycnt = a.dep_cnt[tile * kDepGroups + dl];
-        if (mycnt) a.dep_cnt[tile * kDepGroups + dl] = 0u;
-        if (mycnt > (uint32_t)kDepCap) mycnt = (uint32_t)kDepCap;  // overflowed: the flag is set, nothing is applied
-      }
-      const bool usable = *a.dep_flag == 0u;
-      if (!usable || !__any_sync(kLanes, mycnt != 0u)) return;
-      for (int s = dl; s < kDepHash; s += 31) { hkey[s] = kDepNone; hsum[s] = 0.0f; }
-      __syncwarp(kLanes);
-      const uint32_t* const bins = a.dep_rec + tile * (long long)(kDepGroups * kDepCap);
-      const float amt0 = a.dep_amt[0], amt1 = a.dep_amt[1], amt2 = a.dep_amt[2];
-      uint32_t rec[kDepPerLane];
-      auto fetch = [&](int g) {  // bin of stage group g -> registers (its latency hides behind the next wait)
-        const uint32_t n = g < kDepGroups ? __shfl_sync(kLanes, mycnt, g + 1) : 0u;
-#pragma unroll
-        for (int k = 0; k < kDepPerLane; ++k) {
-          const uint32_t e = (uint32_t)dl + 31u * k;
-          rec[k] = e < n ? __ldcs(bins + g * kDepCap + e) : kDepNone;
+    } else if (DEP && ndep) {
+      // lanes 1..31 (diverged from the producer lane for good; they only meet it at mbarriers)
+      auto dep_stages = [&](int jb, int je) {  // the entries of stages [jb, je): output rows [4 jb - 2, 4 je - 2)
+        const int e1 = dstart[je];
+        for (int e = dstart[jb] + lane - 1; e < e1; e += 31) {
+          const uint32_t dc = dcol[e];  // row << 10 | column, both within the tile
+          atomicAdd(otile + (long long)(dc >> 10) * a.pitch + (dc & 1023u), dsum[e]);
         }
-        return n;
       };
-      auto apply = [&](uint32_t n) {  // totals per cell (exact: small integers), one reduction per touched cell
-        if (n == 0u) return;          // uniform over the deposit lanes
-#pragma unroll
-        for (int k = 0; k < kDepPerLane; ++k) {
-          if (rec[k] == kDepNone) continue;
-          const uint32_t cell = rec[k] & 0xffffu, code = rec[k] >> 16;
-          const float amt = code == 0u ? amt0 : (code == 1u ? amt1 : amt2);
-          uint32_t slot = (cell * 2654435761u) >> 24;
-          while (true) {
-            const uint32_t old = atomicCAS(hkey + slot, kDepNone, cell);
-            if (old == kDepNone || old == cell) { atomicAdd(hsum + slot, amt); break; }
-            slot = (slot + 1u) & (uint32_t)(kDepHash - 1);
-          }
-        }
-        __syncwarp(kLanes);
-        for (int s = dl; s < kDepHash; s += 31) {
-          const uint32_t cell = hkey[s];
-          if (cell != kDepNone) {
-            atomicAdd(otile + (long long)(cell >> 10) * a.pitch + (cell & 1023u), hsum[s]);
-            hkey[s] = kDepNone;
-            hsum[s] = 0.0f;
-          }
-        }
-        __syncwarp(kLanes);
-      };
-      int g = 0;                       // next stage group to apply; rec[] holds its bin
-      uint32_t n = fetch(0);
+      mbar_wait(dep_bar, 0u);
       for (int it = kStages + 1; it < niter; ++it) {
         while (true) {  // stage it - kStages released by every consumer warp?
           uint32_t seen;
@@ -208,14 +173,10 @@ k_stencil_tma(StencilArgs a) {
           if ((int)seen >= it) break;
           __nanosleep(200);
         }
-        apply(n);                      // stage group it - kStages - 1 == g
-        n = fetch(++g);
+        dep_stages(it - kStages - 1, it - kStages);
       }
       mbar_wait(fin, 0u);  // the last kStages + 1 stages, after the consumers' last stores
-      for (; g < niter; ) {
-        apply(n);
-        n = fetch(++g);
-      }
+      dep_stages(max(niter - kStages - 1, 0), niter);
     }
     return;
   }
@@ -278,7 +239,7 @@ k_stencil_tma(StencilArgs a) {
       }
     }
   }
-  if (DEP) {
+  if (DEP && ndep) {
     __syncwarp();
     if (lane == 0) mbar_arrive(fin);
   }
@@ -287,7 +248,7 @@ k_stencil_tma(StencilArgs a) {
 template <int ST, int R, int S, bool PEER, bool DEP = false>
 static int tma_launch_one(TmaStencilState* st, int slot, const StencilArgs& a, dim3 grid, cudaStream_t s) {
   size_t smem = (size_t)S * R * kTmaRowFloats * sizeof(float) + (2 * S + 3) * sizeof(uint64_t);
-  if (DEP) smem = ((smem + 15) & ~(size_t)15) + kDepSmemBytes;
+  if (DEP) smem = ((smem + 15) & ~(size_t)15) + kDepBlkBytes;
   const int sti = ST == 0 ? 0 : (ST == 5 ? 1 : 2);
   if (!st->attr_set[sti][slot]) {
     cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<ST, R, S, PEER, DEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

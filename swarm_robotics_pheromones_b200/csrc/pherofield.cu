@@ -61,7 +61,8 @@ struct pf_handle {
   // owner-computes deposit (pf_deposit_owner.cuh): valid after pf_agents_sort for these arrays
   uint32_t *own_split, *own_cmin, *own_cmax, *own_pmax, *own_smin, *own_body, *own_tail;
   // deposit fused into the stencil (pf_deposit_tile.cuh): per-tile bins, per-tile lists, status flag
-  uint32_t *tile_bcnt, *tile_brec, *tile_flag;
+  uint32_t *tile_bcnt, *tile_brec, *tile_flag, *tile_count;
+  unsigned char* tile_blk;
   long long tile_alloc;   // tiles allocated
   int no_tile_deposit;
   bool tile_pending;      // lists are ready for (pf_step: were given to) the stencil launch over tile_ty0..ty1
@@ -148,7 +149,8 @@ static size_t mig_box_words(long long cap) { return (size_t)(cap + 1) * PF_MIGRA
 static void graph_drop(pf_handle* h);
 
 static void tile_free(pf_handle* h) {
-  void** arrs[3] = {(void**)&h->tile_bcnt, (void**)&h->tile_brec, (void**)&h->tile_flag};
+  void** arrs[5] = {(void**)&h->tile_bcnt, (void**)&h->tile_brec, (void**)&h->tile_flag, (void**)&h->tile_count,
+                    (void**)&h->tile_blk};
   for (auto pp : arrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   h->tile_alloc = 0;
 }
@@ -590,11 +592,9 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, 
   for (int k = 0; k < PF_MAX_CHANNELS; ++k) { a.keep[k] = d.keep[k]; a.dk[k] = d.dk[k]; }
   a.del_thr = d.del_thr;
   a.peer = peer_rows(h, h->cur ^ 1);
-  a.dep_flag = nullptr; a.dep_cnt = nullptr; a.dep_rec = nullptr; a.dep_ty0 = 0; a.dep_ny = 0;
-  a.dep_amt[0] = a.dep_amt[1] = a.dep_amt[2] = 0.0f;
+  a.dep_flag = nullptr; a.dep_count = nullptr; a.dep_blk = nullptr; a.dep_ty0 = 0; a.dep_ny = 0;
   if (with_deposits) {  // tile_ok() / strip_tile_range() hold: whole tile rows, TMA ring, CTA = deposit tile
-    a.dep_flag = h->tile_flag; a.dep_cnt = h->tile_bcnt; a.dep_rec = h->tile_brec;
-    a.dep_amt[0] = d.i_explore; a.dep_amt[1] = d.i_high; a.dep_amt[2] = d.i_homing;
+    a.dep_flag = h->tile_flag; a.dep_count = h->tile_count; a.dep_blk = h->tile_blk;
     int rc = tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, h->tile_ty1, s);
     if (rc != PF_OK) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
     h->launches++;
@@ -730,8 +730,8 @@ static bool tile_common_ok(const pf_handle* h, const pf_agents* a) {
   const PFDev& d = h->dev;
   return !h->no_tile_deposit && !h->overlap_agents && owner_ready(h, a) && d.stencil != 0 && d.dep_red && d.dep_exact &&
          d.W % 4 == 0 && d.W >= 512 && (h->variant == 0 || h->variant == 2) && h->rows_per_cta <= 0 &&
-         kTileRows == kDepRows && kTileCols == kTmaCols && kTileGroups == kDepGroups && kTileGroupCap == kDepCap &&
-         kTileHash == kDepHash && kTileNoRec == kDepNone;
+         kTileRows == kDepRows && kTileEnt == kDepEnt && kTileCols == kTmaCols && kTileBlkBytes == kDepBlkBytes &&
+         kTilePtrBytes == kDepPtrBytes;
 }
 static bool tile_ok(const pf_handle* h, const pf_agents* a) { return !is_sharded(h) && tile_common_ok(h, a); }
 
@@ -777,6 +777,8 @@ static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb, int ty0, int t
     PF_CUDA(h, cudaMalloc(&h->tile_flag, 2 * sizeof(uint32_t)));  // [0] status of this tick, [1] fallbacks so far
     PF_CUDA(h, cudaMemset(h->tile_flag, 0, 2 * sizeof(uint32_t)));
     PF_CUDA(h, cudaMalloc(&h->tile_brec, sizeof(uint32_t) * ntiles * kTileGroups * kTileGroupCap));
+    PF_CUDA(h, cudaMalloc(&h->tile_count, sizeof(uint32_t) * ntiles));
+    PF_CUDA(h, cudaMalloc(&h->tile_blk, (size_t)ntiles * kTileBlkBytes));
     h->tile_alloc = ntiles;
   }
   PF_CUDA(h, cudaMemsetAsync(h->tile_flag, 0, sizeof(uint32_t), s));
@@ -787,10 +789,13 @@ static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb, int ty0, int t
   return PF_OK;
 }
 
-// after the move kernel: nothing to do — the stencil's deposit lanes read the bins themselves (round 1 grouped
-// them into per-tile lists here, 0.36 ms per tick at config 3)
+// after the move kernel: bins -> per-tile lists for the stencil
 static int tile_finish(pf_handle* h, cudaStream_t s) {
-  (void)h; (void)s;
+  const int nx = (h->dev.W + kTileCols - 1) / kTileCols, ny = (h->dev.rows + kTileRows - 1) / kTileRows;
+  const long long ntiles = (long long)nx * ny * h->dev.C;
+  k_tile_group<<<(unsigned)ntiles, kGroupThreads, 0, s>>>(h->tile_bcnt, h->tile_brec, h->tile_flag, h->tile_count,
+                                                          h->tile_blk, h->dev.i_explore, h->dev.i_high, h->dev.i_homing);
+  PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
 
