@@ -428,6 +428,9 @@ int pf_trail_set_state(pf_trail* t, int64_t robot, int state);
 /* one supervisor tick for every robot: pos_xyz [n][3] and ps [n][8] are device fp64 arrays */
 int pf_trail_tick(pf_trail* t, double t_now, double start_delay, const double* pos_xyz,
                   const double* ps, const pf_trail_out* out, void* stream);
+/* PF_ESTATE (and *n_dropped > 0) once a deposit found a robot's live list full: from then on the sense results no
+ * longer match the reference's dict. Synchronises the stream. */
+int pf_trail_dropped(pf_trail* t, uint64_t* n_dropped, void* stream);
 int pf_trail_entries(pf_trail* t, double** time, double** intensity, double** x, double** y,
                      double** z, int** n_live, int* capacity);
 

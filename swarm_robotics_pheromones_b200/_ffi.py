@@ -69,6 +69,7 @@ SIGNATURES = {
     "pf_trail_configure": (C.c_int, [_vp, _vp, _vp, _vp]),
     "pf_trail_set_state": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "pf_trail_tick": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, C.POINTER(abi.PFTrailOut), _vp]),
+    "pf_trail_dropped": (C.c_int, [_vp, C.POINTER(C.c_uint64), _vp]),
     "pf_trail_entries": (C.c_int, [_vp] + [C.POINTER(_vp)] * 6 + [C.POINTER(C.c_int)]),
     "pf_heatmap_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
     "pf_heatmap_destroy": (C.c_int, [_vp]),
@@ -105,6 +106,9 @@ def lib() -> C.CDLL:
                 raise RuntimeError(
                     f"libpherofield.so is not built and cannot be built here ({e}); "
                     "pherofield has no CPU fallback") from e
+            import warnings
+            warnings.warn(f"libpherofield.so is older than its sources and could not be rebuilt ({e}); "
+                          "loading the existing library", RuntimeWarning)
     L = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(L, name)  # AttributeError = symbol missing: fail loudly

@@ -52,9 +52,25 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
     LIB_DIR.mkdir(exist_ok=True)
-    cmd = [nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, sources())]
+    # one builder at a time (every torchrun rank may get here at once on a fresh clone), and the library
+    # appears atomically: nvcc writes a temporary file that is renamed into place
+    import fcntl
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():      # another process built it while this one waited
+            return LIB
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> Path:
+    tmp = LIB_DIR / f".libpherofield.{os.getpid()}.so"
+    cmd = [nvcc(), *NVCC_FLAGS, "-o", str(tmp), *map(str, sources())]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     (LIB_DIR / "build.log").write_text(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if proc.returncode == 0:
+        os.replace(tmp, LIB)
+    elif tmp.exists():
+        tmp.unlink()
     if proc.returncode != 0:
         errs = [ln for ln in (proc.stdout + proc.stderr).splitlines() if "error" in ln.lower()]
         sys.stderr.write("\n".join(errs[:40]) + f"\n(full log: {LIB_DIR / 'build.log'})\n")

@@ -640,47 +640,49 @@ k_migrate_find(long long n, int nc, const uint32_t* __restrict__ emp_base, const
                const uint32_t* __restrict__ buf2, long long cap, const uint32_t* __restrict__ ameta,
                const uint32_t* __restrict__ body_chunks, long long* __restrict__ slot_of) {
   const int lane = threadIdx.x & 31;
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // record index over both buffers
   unsigned long long m1 = buf ? buf[0] : 0ull, m2 = buf2 ? buf2[0] : 0ull;
   if (m1 > (unsigned long long)cap) m1 = cap;
   if (m2 > (unsigned long long)cap) m2 = cap;
-  if ((unsigned long long)w >= m1 + m2) return;
-  if (lane == 0) slot_of[w] = -1;
   const unsigned long long empties = emp_base[nc];
-  unsigned long long r;  // candidate rank among the free slots
-  if ((unsigned long long)w < m1) {
-    r = (unsigned long long)w;
-    if (r >= empties) return;  // no room: dropped (counted in k_empty_offsets)
-  } else {
-    const unsigned long long back = (unsigned long long)w - m1;  // 0 takes the highest free slot
-    if (back >= empties || empties - 1 - back < m1) return;     // the ascending records keep theirs
-    r = empties - 1 - back;
-  }
-  int lo = 0, hi = nc;  // last chunk with emp_base[c] <= r
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if ((unsigned long long)emp_base[mid] <= r) lo = mid; else hi = mid;
-  }
   long long T, M;
   mig_body_split(body_chunks, n, T, M);
-  unsigned need = (unsigned)(r - emp_base[lo]);  // free slots of this chunk to skip
-  long long slot = -1;
-  for (int k = 0; k < kOwnChunk / 32; ++k) {
-    const long long ip = (long long)lo * kOwnChunk + 32 * k + lane;
-    const long long i = ip < n ? mig_slot_of_rank_index(ip, n, T, M) : -1;
-    const bool empty = i >= 0 && (ameta[i] & PF_META_STATE_MASK) == PF_STATE_EMPTY;
-    const unsigned m = __ballot_sync(0xffffffffu, empty);
-    const unsigned c = (unsigned)__popc(m);
-    if (need < c) {  // the need-th set bit of m
-      unsigned mm = m;
-      for (unsigned z = 0; z < need; ++z) mm &= mm - 1u;
-      const int src = __ffs(mm) - 1;
-      slot = __shfl_sync(0xffffffffu, i, src);
-      break;
+  // a small grid strides over the records that actually arrived (a few thousand out of 2 * cap)
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; (unsigned long long)w < m1 + m2; w += nwarps) {
+    if (lane == 0) slot_of[w] = -1;
+    unsigned long long r;  // candidate rank among the free slots
+    if ((unsigned long long)w < m1) {
+      r = (unsigned long long)w;
+      if (r >= empties) continue;  // no room: dropped (counted in k_empty_offsets)
+    } else {
+      const unsigned long long back = (unsigned long long)w - m1;  // 0 takes the highest free slot
+      if (back >= empties || empties - 1 - back < m1) continue;   // the ascending records keep theirs
+      r = empties - 1 - back;
     }
-    need -= c;
+    int lo = 0, hi = nc;  // last chunk with emp_base[c] <= r
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((unsigned long long)emp_base[mid] <= r) lo = mid; else hi = mid;
+    }
+    unsigned need = (unsigned)(r - emp_base[lo]);  // free slots of this chunk to skip
+    long long slot = -1;
+    for (int k = 0; k < kOwnChunk / 32; ++k) {
+      const long long ip = (long long)lo * kOwnChunk + 32 * k + lane;
+      const long long i = ip < n ? mig_slot_of_rank_index(ip, n, T, M) : -1;
+      const bool empty = i >= 0 && (ameta[i] & PF_META_STATE_MASK) == PF_STATE_EMPTY;
+      const unsigned m = __ballot_sync(0xffffffffu, empty);
+      const unsigned c = (unsigned)__popc(m);
+      if (need < c) {  // the need-th set bit of m
+        unsigned mm = m;
+        for (unsigned z = 0; z < need; ++z) mm &= mm - 1u;
+        const int src = __ffs(mm) - 1;
+        slot = __shfl_sync(0xffffffffu, i, src);
+        break;
+      }
+      need -= c;
+    }
+    if (lane == 0) slot_of[w] = slot;
   }
-  if (lane == 0) slot_of[w] = slot;
 }
 
 // one thread per arriving record

@@ -32,6 +32,7 @@ struct pf_trail {
   unsigned char* state;
   double* start;  // [3][n]
   double food[3];
+  unsigned long long* dropped;  // deposits that found the robot's live list full (capacity too small)
   unsigned long long launches;
   char err[256];
 };
@@ -72,7 +73,8 @@ k_trail_tick(long long n, int cap, double t_now, double start_delay, const doubl
              const double* __restrict__ ps, double* et, double* ei, double* ex, double* ey, double* ez,
              int* n_live_a, int* n_global_a, double* cur, double* prev, unsigned char* have,
              double* wl_a, double* wr_a, const unsigned char* __restrict__ state_a,
-             const double* __restrict__ start, double fx, double fy, TrailOut o) {
+             const double* __restrict__ start, double fx, double fy, TrailOut o,
+             unsigned long long* __restrict__ dropped) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int st = state_a[r];
@@ -126,6 +128,8 @@ k_trail_tick(long long n, int cap, double t_now, double start_delay, const doubl
     if (slot < cap) {
       E(et, slot) = t_now; E(ei, slot) = amount; E(ex, slot) = px; E(ey, slot) = py; E(ez, slot) = pz;
       if (!same_key) nl += 1;
+    } else {
+      atomicAdd(dropped, 1ull);  // live list full: the reference's dict would have grown (pf_trail_dropped)
     }
     n_global_a[r] = ng;
   }
@@ -261,7 +265,7 @@ extern "C" int pf_trail_destroy(pf_trail* t) {
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {t->et, t->ei, t->ex, t->ey, t->ez, t->n_live, t->n_global, t->cur, t->prev,
-                  t->have, t->wl, t->wr, t->state, t->start};
+                  t->have, t->wl, t->wr, t->state, t->start, t->dropped};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete t;
@@ -299,6 +303,7 @@ extern "C" int pf_trail_create(int device, int64_t n_robots, int capacity, pf_tr
   TR_ALLOC(cur, 3 * n * sizeof(double)); TR_ALLOC(prev, 3 * n * sizeof(double));
   TR_ALLOC(have, n); TR_ALLOC(wl, n * sizeof(double)); TR_ALLOC(wr, n * sizeof(double));
   TR_ALLOC(state, n); TR_ALLOC(start, 3 * n * sizeof(double));
+  TR_ALLOC(dropped, sizeof(unsigned long long));
 #undef TR_ALLOC
   TR_CUDA(t, cudaMemset(t->state, PF_STATE_SEARCHING, n));
   *out = t;
@@ -349,9 +354,27 @@ extern "C" int pf_trail_tick(pf_trail* t, double t_now, double start_delay, cons
   k_trail_tick<<<grid, 128, 0, (cudaStream_t)stream>>>(t->n, t->cap, t_now, start_delay, pos_xyz, ps, t->et,
                                                       t->ei, t->ex, t->ey, t->ez, t->n_live, t->n_global,
                                                       t->cur, t->prev, t->have, t->wl, t->wr, t->state,
-                                                      t->start, t->food[0], t->food[1], o);
+                                                      t->start, t->food[0], t->food[1], o, t->dropped);
   TR_CUDA(t, cudaGetLastError());
   t->launches++;
+  return PF_OK;
+}
+
+// Deposits lost so far because a robot's live list was full (capacity <= 64 entries; the shipped supervisor
+// peaks near 51 at dt = 0.064 s, a 32 ms tick or slower evaporation needs more): > 0 means sense results no
+// longer match the reference's dict. Synchronises the stream.
+extern "C" int pf_trail_dropped(pf_trail* t, uint64_t* n_dropped, void* stream) {
+  if (!t || !n_dropped) return PF_EINVAL;
+  TR_CUDA(t, cudaSetDevice(t->device));
+  unsigned long long v = 0;
+  TR_CUDA(t, cudaMemcpyAsync(&v, t->dropped, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  TR_CUDA(t, cudaStreamSynchronize((cudaStream_t)stream));
+  *n_dropped = v;
+  if (v) {
+    snprintf(t->err, sizeof(t->err), "%llu deposits did not fit a robot's live list (capacity %d): results differ "
+             "from the reference's dict from that tick on", v, t->cap);
+    return PF_ESTATE;
+  }
   return PF_OK;
 }
 

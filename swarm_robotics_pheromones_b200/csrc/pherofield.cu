@@ -1356,8 +1356,11 @@ extern "C" int pf_migrate_unpack2(pf_handle* h, const pf_agents* a, const uint32
   k_empty_offsets<<<1, 1024, 0, s>>>(nc, cap, h->emp_cnt, h->emp_base, buf, buf2, h->counters);
   PF_LAUNCH_CHECK(h);
   // one warp per record that may arrive (the headers stay on the device: the grid covers 2 * cap)
-  k_migrate_find<<<blocks_for(2 * cap * 32, 256), 256, 0, s>>>(a->n, nc, h->emp_base, buf, buf2, cap, a->meta, body,
+  {
+    const unsigned want = blocks_for(2 * cap * 32, 256), wave = (unsigned)(2 * h->n_sm);
+  k_migrate_find<<<want < wave ? want : wave, 256, 0, s>>>(a->n, nc, h->emp_base, buf, buf2, cap, a->meta, body,
                                                                h->mig_slot_of);
+  }
   PF_LAUNCH_CHECK(h);
   k_migrate_fill<<<blocks_for(2 * cap, 256), 256, 0, s>>>(buf, buf2, cap, h->mig_slot_of, a->x, a->y, a->theta,
                                                           a->wl, a->wr, a->meta, a->gid);

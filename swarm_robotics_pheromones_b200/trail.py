@@ -95,6 +95,12 @@ class TrailSwarm:
                                        self.ps.data_ptr(), C.byref(self._out_struct), s))
         return self.out
 
+    def check_capacity(self):
+        """raises PFError(PF_ESTATE) once a deposit did not fit a robot's live list (was silent)"""
+        n = C.c_uint64()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self._ck(self._L.pf_trail_dropped(self._h, C.byref(n), s))
+
     # ---- live entries of one robot, as the reference's dict -----------------------------------
     def _entries(self, i: int):
         ptrs = [C.c_void_p() for _ in range(6)]
@@ -133,6 +139,7 @@ class TrailSwarm:
             t_now = self.time
         names = self.names if robot_names is None else [nm for nm in robot_names if nm in self.index]
         out = self.tick_device(t_now)
+        self.check_capacity()
         host = {k: v.cpu().numpy() for k, v in out.items()}
         res = {}
         for name in names:

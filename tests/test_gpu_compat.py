@@ -136,3 +136,20 @@ def test_tick_host_equals_oracle_without_move():
         assert (wl.numpy().view(np.uint32) == a.wl.view(np.uint32)).all()
     assert (rc.field.snapshot().view(np.uint32) == np.ascontiguousarray(o.field).view(np.uint32)).all()
     rc.close()
+
+
+def test_first_deposit_after_the_start_delay_is_unconditional_for_a_stationary_robot():
+    # the reference stores poses only inside deposit_pheromone (sup:279-289, called from t >= 5 s on), so
+    # the first deposit has no previous pose and is unconditional (old_pos is None -> True, sup:261-262) — even for a
+    # robot that has not moved since t = 0. The second tick then sees no movement: "nothing deposited" (sup:321-322)
+    cfg = c0_config()
+    rc = ReferenceCompat(cfg, ["e1", "e2"], [[0.1, 0.1, 0.0], [-0.2, 0.3, 0.0]], start_delay=5.0, time0=4.8)
+    pose = torch.empty((3, 2)).pin_memory()
+    pose[0] = torch.tensor([0.1, -0.2]); pose[1] = torch.tensor([0.1, 0.3]); pose[2] = 0.0
+    deposits = []
+    for _ in range(6):                      # t = 4.8, 4.864, 4.928, 4.992 (random walk), 5.056, 5.12 (pheromone ticks)
+        rc.tick_host(pose)
+        torch.cuda.synchronize()
+        deposits.append(int(rc.field.counters().deposits))
+    assert deposits == [0, 0, 0, 0, 2, 2], deposits
+    rc.close()

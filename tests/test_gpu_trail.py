@@ -76,3 +76,19 @@ def test_many_robots_same_trace_and_start_delay(golden_dir):
         for name in (names[0], names[100], names[-1]):
             _check(out[name], rec, f"{name} t={rec['t']}")
     sw.close()
+
+
+def test_full_live_list_is_reported_not_silent():
+    # a deposit that finds the robot's live list full used to be dropped silently. With a capacity of
+    # 8 entries the ninth deposit (entries only start to evaporate after 2 s) raises PF_ESTATE through TrailSwarm
+    from swarm_robotics_pheromones_b200 import abi
+    from swarm_robotics_pheromones_b200._ffi import PFError
+    sw = TrailSwarm(["e2"], [[0.0, 0.0, 0.0]], [0.36, -0.15, 0.05], ps=60.0, start_delay=0.0, capacity=8)
+    t, y = 0.0, 0.0
+    with pytest.raises(PFError) as e:
+        for _ in range(12):
+            y += 0.004
+            sw.startPheromone(["e2"], {"e2": [0.0, y, 0.0]}, t_now=t)
+            t += 0.064
+    assert e.value.code == abi.PF_ESTATE and "live list" in str(e.value)
+    sw.close()
