@@ -364,7 +364,9 @@ def measure_other_config(name, steps, sort_every=16):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     c = f.counters()
-    out = {"workload": f"{name}: {cfg.H}x{cfg.W}x{cfg.C}, {n} agents, {cfg.stencil}-point",
+    att, fb = f.tile_stats()
+    out = {"fused_deposit": {"ticks_attempted": att, "ticks_fell_back": fb, "dense_tiles": f.tile_dense()[0]},
+           "workload": f"{name}: {cfg.H}x{cfg.W}x{cfg.C}, {n} agents, {cfg.stencil}-point",
            "steps": steps, "ms_per_step": ms, "cell_updates_per_s": cells / (ms * 1e-3),
            "agent_steps_per_s": n / (ms * 1e-3),
            "whole_tick_GBs": (cells * 8 + n * 76 + 8 * min(n, cells)) / (ms * 1e-3) / 1e9}
@@ -483,6 +485,8 @@ def run_single(args):
         torch.cuda.synchronize()
     prof = field.profile_read(reset=True)
     field.profile(False)
+    tile_att, tile_fb = field.tile_stats()
+    tile_dense = field.tile_dense()
     ms_per_step = ms / args.steps
     value = cells * args.steps / (ms * 1e-3)
     agent_rate = n * args.steps / (ms * 1e-3)
@@ -568,6 +572,8 @@ def run_single(args):
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
         "stencil_variant": args.variant, "agent_sort_every": args.sort_every,
         "agent_sorts_in_timed_region": sorts_timed,
+        "fused_deposit": {"ticks_attempted": tile_att, "ticks_fell_back": tile_fb, "dense_tiles": tile_dense[0],
+                          "dense_tile_buffers": tile_dense[1]},
         "other_configs": others, "sparse_trail_engine": trail_eng,
     }
     emit(line)
@@ -820,7 +826,7 @@ def main():
     ap.add_argument("--rows-per-cta", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--sort-every", type=int, default=16,
+    ap.add_argument("--sort-every", type=int, default=32,
                     help="re-order the agent arrays by cell every this many ticks (0 = never)")
     ap.add_argument("--overlap-agents", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -382,6 +382,10 @@ int pf_tile_rows(pf_handle* h, const pf_agents* a, int* row_begin, int* row_end)
  * those fell back on the device to the separate deposit kernels (a tile too crowded).
  * Synchronises the device. */
 int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_back);
+/* Crowded tiles since the last pf_agents_sort: tiles (channel x 64 rows x 1024 columns) whose deposits no longer fit the
+ * per-tile lists (more than one robot per few cells, e.g. a nest) and go through a per-cell side buffer instead, and
+ * the number of such buffers available. Synchronises the device. */
+int pf_tile_dense(pf_handle* h, uint64_t* n_dense, uint64_t* pool_slots);
 
 /* Per-phase device times of pf_step, from CUDA events recorded on the launching streams while
  * profiling is enabled (bench.py's live roofline numbers). Times are sums over `ticks` ticks. */

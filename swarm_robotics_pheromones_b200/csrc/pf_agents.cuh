@@ -418,7 +418,10 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
             owner_note_bounds(cmin, cmax, i / kOwnChunk, key % plane, key != sentinel);
           }
         }
-        if (tb.bcnt) tile_bin_put(tb, __activemask(), tile, tile_record(local, code));
+        if (tb.bcnt) {
+          if (tile_side_put(tb, tile, local, amt)) tile = -1;  // dense tile: already added to its side buffer
+          tile_bin_put(tb, __activemask(), tile, tile_record(local, code));
+        }
       }
       ameta[i] = nm;
       if (dec_out) dec_out[i] = (uint8_t)dec;

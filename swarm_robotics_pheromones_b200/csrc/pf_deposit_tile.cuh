@@ -64,10 +64,21 @@ __device__ __forceinline__ uint32_t tile_record(uint32_t local_cell, uint32_t am
   return local_cell | (amount_code << 16);
 }
 
+// Crowded tiles (config 4's nest: more than one robot per cell): a tile whose bin overflowed is marked DENSE and
+// gets a side buffer of one fp32 total per cell (64 x 1024 x 4 B = 256 KB out of a small pool). From the next tick
+// on the move kernel adds that tile's amounts straight into the side buffer (reductions performed by the L2: exact,
+// the amounts are small integers), and the tile's stencil CTA adds the buffer to its output rows as it stores them
+// and clears it. No sort, no grouping for those tiles; marks are reset by pf_agents_sort.
+constexpr int kTileCells = kTileRows * kTileCols;
+
 struct TileBins {
   uint32_t* bcnt;  // [tile * kTileGroups + g] records in the bin; null: no binning
   uint32_t* brec;  // [(tile * kTileGroups + g) * kTileGroupCap + k]
   uint32_t* flag;
+  int* dense;      // [tile] side buffer slot, -1 = sparse (bins), -2 = being marked
+  float* side;     // [slot][kTileCells]
+  uint32_t* pool;  // [0] slots handed out so far
+  int pool_cap;
   int nx, ny;      // tiles along a row / along a column of one channel plane
   int ty_lo, ty_hi;  // tile rows whose deposits the stencil takes (all of them on one GPU; on a strip
                      // the interior ones that the stencil writes after the move kernel)
@@ -84,9 +95,26 @@ __device__ __forceinline__ void tile_bin_put(const TileBins& tb, unsigned act, i
     if (lane == leader) base = atomicAdd(tb.bcnt + bin, (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    if (pos < (uint32_t)kTileGroupCap) tb.brec[(long long)bin * kTileGroupCap + pos] = rec;
-    else *tb.flag = 1u;
+    if (pos < (uint32_t)kTileGroupCap) {
+      tb.brec[(long long)bin * kTileGroupCap + pos] = rec;
+    } else {  // this tick falls back to the regular deposit kernels; from the next one on the tile is dense
+      *tb.flag = 1u;
+      const int tile = bin / kTileGroups;
+      if (tb.dense && atomicCAS(tb.dense + tile, -1, -2) == -1) {
+        const uint32_t slot = atomicAdd(tb.pool, 1u);
+        tb.dense[tile] = slot < (uint32_t)tb.pool_cap ? (int)slot : -1;  // pool exhausted: stays sparse (and falls back)
+      }
+    }
   }
+}
+
+// dense tile: the amount goes straight into the tile's side buffer; returns true if it did
+__device__ __forceinline__ bool tile_side_put(const TileBins& tb, int bin, uint32_t local, float amt) {
+  if (bin < 0 || !tb.dense) return false;
+  const int slot = tb.dense[bin / kTileGroups];
+  if (slot < 0) return false;
+  atomicAdd(tb.side + (long long)slot * kTileCells + local, amt);
+  return true;
 }
 
 // bin (tile and stage group) and cell-within-tile of (channel, strip-local row, column); -1 if the
@@ -106,7 +134,8 @@ constexpr int kGroupPerLane = (kTileGroupCap + 31) / 32;
 
 __global__ void __launch_bounds__(kGroupThreads, 6)
 k_tile_group(uint32_t* __restrict__ bcnt, const uint32_t* __restrict__ brec, uint32_t* __restrict__ flag,
-             uint32_t* __restrict__ tcount, unsigned char* __restrict__ tblk, float amt0, float amt1, float amt2) {
+             uint32_t* __restrict__ tcount, unsigned char* __restrict__ tblk, float amt0, float amt1, float amt2,
+             int* __restrict__ dense, uint32_t* __restrict__ pool, int pool_cap) {
   __shared__ uint32_t hkey[kTileGroups + 1][kTileHash];
   __shared__ float hsum[kTileGroups + 1][kTileHash];
   __shared__ uint32_t gcnt[32], gstart[32], total_s;
@@ -186,8 +215,20 @@ k_tile_group(uint32_t* __restrict__ bcnt, const uint32_t* __restrict__ brec, uin
       reinterpret_cast<uint16_t*>(blk)[t] = (uint16_t)(inc - c);  // start[kTileGroups] = total
     if (t == 0) {
       total_s = total;
-      if (total > (uint32_t)kTileEnt) *flag = 1u;
-      else tcount[tile] = total;
+      if (total > (uint32_t)kTileEnt) {  // too many distinct cells for one list: fall back this tick, dense from the next
+        *flag = 1u;
+        if (dense && atomicCAS(dense + tile, -1, -2) == -1) {
+          const uint32_t slot = atomicAdd(pool, 1u);
+          dense[tile] = slot < (uint32_t)pool_cap ? (int)slot : -1;
+        }
+      } else {
+        tcount[tile] = total;
+        // getting close to the list's capacity: dense from the next tick on, without a fall-back in between
+        if (dense && total > (uint32_t)(kTileEnt * 3 / 4) && atomicCAS(dense + tile, -1, -2) == -1) {
+          const uint32_t slot = atomicAdd(pool, 1u);
+          dense[tile] = slot < (uint32_t)pool_cap ? (int)slot : -1;
+        }
+      }
     }
   }
   __syncthreads();

@@ -33,6 +33,8 @@ struct StencilArgs {
   const uint32_t* dep_count;  // [tile] entries
   const unsigned char* dep_blk;  // [tile] start[] / col[] / sum[] block
   int dep_ty0, dep_ny;           // tile row of this launch's first CTA row; tile rows per channel
+  const int* dep_dense;          // [tile] side buffer slot of a crowded tile, < 0 = none (pf_deposit_tile.cuh)
+  float* dep_side;               // [slot][64 * 1024] per-cell totals: added to the output rows, then cleared
 };
 
 // per-channel constant without dynamic indexing of the kernel parameter block (which would make

@@ -104,9 +104,15 @@ k_stencil_tma(StencilArgs a) {
 
   uint32_t ndep = 0u;
   long long tile = 0;
+  float* side = nullptr;      // crowded tile: per-cell totals to add to the output (uniform per CTA)
+  bool side_add = false;
   if (DEP) {
     tile = ((long long)ch * a.dep_ny + a.dep_ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (*a.dep_flag == 0u) ndep = a.dep_count[tile];  // uniform per CTA
+    const bool usable = *a.dep_flag == 0u;
+    if (usable) ndep = a.dep_count[tile];  // uniform per CTA
+    const int slot = a.dep_dense ? a.dep_dense[tile] : -1;
+    if (slot >= 0) side = a.dep_side + (long long)slot * (kDepRows * kTmaCols);
+    side_add = usable;   // a tick that fell back only clears the buffer: the regular deposit kernels redo it
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -227,6 +233,19 @@ k_stencil_tma(StencilArgs a) {
         if (si >= 2) {
           const int rr = r0 + si - 2;
           float4 o = stencil_vec<ST>(qn.v, qc.v, rows[k].v, cw, ce, nw, ne, sw, se, keep, dk, thr);
+          if (DEP && side && live) {  // crowded tile: next tick's totals of this row segment, touched cells only
+            float4* sp = reinterpret_cast<float4*>(side + (long long)(rr - r0) * kTmaCols + 4 * t);
+            const float4 sv = __ldcg(sp);
+            if (sv.x != 0.f || sv.y != 0.f || sv.z != 0.f || sv.w != 0.f) {
+              __stcg(sp, make_float4(0.f, 0.f, 0.f, 0.f));
+              if (side_add) {
+                if (sv.x != 0.f) o.x = fadd(o.x, sv.x);
+                if (sv.y != 0.f) o.y = fadd(o.y, sv.y);
+                if (sv.z != 0.f) o.z = fadd(o.z, sv.z);
+                if (sv.w != 0.f) o.w = fadd(o.w, sv.w);
+              }
+            }
+          }
           if (live) *reinterpret_cast<float4*>(obase + (long long)rr * a.pitch + col4) = o;
           if (PEER) {
             if (peer_first && rr == 0) *reinterpret_cast<float4*>(peer_first) = o;

@@ -61,8 +61,11 @@ struct pf_handle {
   // owner-computes deposit (pf_deposit_owner.cuh): valid after pf_agents_sort for these arrays
   uint32_t *own_split, *own_cmin, *own_cmax, *own_pmax, *own_smin, *own_body, *own_tail;
   // deposit fused into the stencil (pf_deposit_tile.cuh): per-tile bins, per-tile lists, status flag
-  uint32_t *tile_bcnt, *tile_brec, *tile_flag, *tile_count;
+  uint32_t *tile_bcnt, *tile_brec, *tile_flag, *tile_count, *tile_pool;
   unsigned char* tile_blk;
+  int* tile_dense;        // [tile] side-buffer slot of a crowded tile (pf_deposit_tile.cuh), -1 = none
+  float* tile_side;       // [tile_pool_cap][64 * 1024]
+  int tile_pool_cap;
   long long tile_alloc;   // tiles allocated
   int no_tile_deposit;
   bool tile_pending;      // lists are ready for (pf_step: were given to) the stencil launch over tile_ty0..ty1
@@ -149,8 +152,8 @@ static size_t mig_box_words(long long cap) { return (size_t)(cap + 1) * PF_MIGRA
 static void graph_drop(pf_handle* h);
 
 static void tile_free(pf_handle* h) {
-  void** arrs[5] = {(void**)&h->tile_bcnt, (void**)&h->tile_brec, (void**)&h->tile_flag, (void**)&h->tile_count,
-                    (void**)&h->tile_blk};
+  void** arrs[8] = {(void**)&h->tile_bcnt, (void**)&h->tile_brec, (void**)&h->tile_flag, (void**)&h->tile_count,
+                    (void**)&h->tile_blk, (void**)&h->tile_pool, (void**)&h->tile_dense, (void**)&h->tile_side};
   for (auto pp : arrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   h->tile_alloc = 0;
 }
@@ -593,8 +596,10 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, 
   a.del_thr = d.del_thr;
   a.peer = peer_rows(h, h->cur ^ 1);
   a.dep_flag = nullptr; a.dep_count = nullptr; a.dep_blk = nullptr; a.dep_ty0 = 0; a.dep_ny = 0;
+  a.dep_dense = nullptr; a.dep_side = nullptr;
   if (with_deposits) {  // tile_ok() / strip_tile_range() hold: whole tile rows, TMA ring, CTA = deposit tile
     a.dep_flag = h->tile_flag; a.dep_count = h->tile_count; a.dep_blk = h->tile_blk;
+    a.dep_dense = h->tile_dense; a.dep_side = h->tile_side;
     int rc = tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, h->tile_ty1, s);
     if (rc != PF_OK) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
     h->launches++;
@@ -723,6 +728,19 @@ extern "C" int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_b
   return PF_OK;
 }
 
+extern "C" int pf_tile_dense(pf_handle* h, uint64_t* n_dense, uint64_t* pool_slots) {
+  if (!h) return PF_EINVAL;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  uint32_t n = 0;
+  if (h->tile_pool) {
+    PF_CUDA(h, cudaDeviceSynchronize());
+    PF_CUDA(h, cudaMemcpy(&n, h->tile_pool, sizeof(n), cudaMemcpyDeviceToHost));
+  }
+  if (n_dense) *n_dense = n < (uint32_t)h->tile_pool_cap ? n : (uint32_t)h->tile_pool_cap;
+  if (pool_slots) *pool_slots = (uint64_t)h->tile_pool_cap;
+  return PF_OK;
+}
+
 // Can this tick's stencil apply the next tick's deposits (pf_deposit_tile.cuh)? Needs the sort-free
 // deposit (its kernels are the device-side fallback), the TMA stencil in its default shape on the
 // whole field, and no second stream.
@@ -779,10 +797,19 @@ static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb, int ty0, int t
     PF_CUDA(h, cudaMalloc(&h->tile_brec, sizeof(uint32_t) * ntiles * kTileGroups * kTileGroupCap));
     PF_CUDA(h, cudaMalloc(&h->tile_count, sizeof(uint32_t) * ntiles));
     PF_CUDA(h, cudaMalloc(&h->tile_blk, (size_t)ntiles * kTileBlkBytes));
+    // side buffers for crowded tiles: a pool of 256 KB blocks, at most 512 (128 MB) or one per tile
+    h->tile_pool_cap = (int)(ntiles < 512 ? ntiles : 512);
+    PF_CUDA(h, cudaMalloc(&h->tile_pool, sizeof(uint32_t)));
+    PF_CUDA(h, cudaMemset(h->tile_pool, 0, sizeof(uint32_t)));
+    PF_CUDA(h, cudaMalloc(&h->tile_dense, sizeof(int) * ntiles));
+    PF_CUDA(h, cudaMemset(h->tile_dense, 0xff, sizeof(int) * ntiles));
+    PF_CUDA(h, cudaMalloc(&h->tile_side, sizeof(float) * (size_t)h->tile_pool_cap * kTileCells));
+    PF_CUDA(h, cudaMemset(h->tile_side, 0, sizeof(float) * (size_t)h->tile_pool_cap * kTileCells));
     h->tile_alloc = ntiles;
   }
   PF_CUDA(h, cudaMemsetAsync(h->tile_flag, 0, sizeof(uint32_t), s));
   tb->bcnt = h->tile_bcnt; tb->brec = h->tile_brec;
+  tb->dense = h->tile_dense; tb->side = h->tile_side; tb->pool = h->tile_pool; tb->pool_cap = h->tile_pool_cap;
   tb->flag = h->tile_flag; tb->nx = nx; tb->ny = ny; tb->ty_lo = ty0; tb->ty_hi = ty1;
   h->tile_ty0 = ty0;
   h->tile_ty1 = ty1;
@@ -794,7 +821,8 @@ static int tile_finish(pf_handle* h, cudaStream_t s) {
   const int nx = (h->dev.W + kTileCols - 1) / kTileCols, ny = (h->dev.rows + kTileRows - 1) / kTileRows;
   const long long ntiles = (long long)nx * ny * h->dev.C;
   k_tile_group<<<(unsigned)ntiles, kGroupThreads, 0, s>>>(h->tile_bcnt, h->tile_brec, h->tile_flag, h->tile_count,
-                                                          h->tile_blk, h->dev.i_explore, h->dev.i_high, h->dev.i_homing);
+                                                          h->tile_blk, h->dev.i_explore, h->dev.i_high, h->dev.i_homing,
+                                                          h->tile_dense, h->tile_pool, h->tile_pool_cap);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -1245,6 +1273,11 @@ extern "C" int pf_agents_sort(pf_handle* h, const pf_agents* a, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = a->n;
   h->mig_flags_n = 0;
+  if (h->tile_dense) {  // crowded-tile marks are re-learnt after every re-sort (their side buffers are empty here:
+                        // every stencil launch that follows a binning move kernel drains them)
+    PF_CUDA(h, cudaMemsetAsync(h->tile_dense, 0xff, sizeof(int) * h->tile_alloc, s));
+    PF_CUDA(h, cudaMemsetAsync(h->tile_pool, 0, sizeof(uint32_t), s));
+  }
   uint32_t* keys_in = (uint32_t*)h->scratch;
   uint32_t* keys_out = keys_in + h->cap;
   uint32_t* idx_in = keys_out + h->cap;

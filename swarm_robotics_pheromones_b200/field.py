@@ -325,6 +325,12 @@ class PheroField:
         self._ck(self._L.pf_tile_stats(self._h, C.byref(a), C.byref(f)))
         return a.value, f.value
 
+    def tile_dense(self):
+        """(crowded tiles that deposit through a side buffer, side buffers available)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.pf_tile_dense(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def profile(self, on: bool):
         self._ck(self._L.pf_profile_enable(self._h, 1 if on else 0))
 

@@ -596,10 +596,11 @@ def test_deposit_riding_on_the_stencil_bitexact(stencil, amounts):
     g.close(); g2.close()
 
 
-def test_deposit_riding_on_the_stencil_falls_back_when_a_tile_is_crowded():
+def test_deposit_riding_on_the_stencil_crowded_tile_falls_back_once_then_goes_dense():
     # 5000 agents inside one tile, 1500 of them on a 4 x 4 patch (the bins of its stage groups overflow):
     # the flag is raised on the device, the stencil leaves its output alone and the next
-    # tick's own deposit kernels do the work — same bits either way
+    # tick's own deposit kernels do the work; the tile is marked dense and from then on its amounts go through
+    # a per-cell side buffer that the tile's stencil CTA adds to its output — same bits either way
     cfg = make_cfg(128, 2048, 1, 9)
     rng = np.random.default_rng(78)
     n = 9000
@@ -620,6 +621,12 @@ def test_deposit_riding_on_the_stencil_falls_back_when_a_tile_is_crowded():
         g.step(sw, k)
         assert_bitexact(g.snapshot(), o.field, "field with crowded tiles")
     attempted, fell_back = g.tile_stats()
-    assert attempted == 2 + 19 and fell_back == attempted
+    assert attempted == 2 + 19 and fell_back == 1   # the first hand-over overflowed; the crowded tile is dense since
     assert g.counters().deposits == int(o.counters[8])
+    # a re-sort forgets the marks: one more fall-back, then dense again
+    g.sort_agents(sw)
+    o.tick(a_np, 6)
+    g.step(sw, 6)
+    assert_bitexact(g.snapshot(), o.field, "field with crowded tiles after a re-sort")
+    assert g.tile_stats() == (2 + 19 + 5, 2)
     g.close()
