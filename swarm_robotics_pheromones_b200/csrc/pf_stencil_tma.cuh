@@ -70,7 +70,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // its (cell, sum) list arrives by two more bulk copies and the producer warp adds them to the rows
 // the consumers have just stored (reductions performed by the L2).
 template <int ST, int kStageRows, int kStages, bool PEER, bool DEP>
-__global__ void __launch_bounds__(kTmaThreads)
+__global__ void __launch_bounds__(kTmaThreads, DEP ? 3 : 1)
 k_stencil_tma(StencilArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
@@ -329,17 +329,26 @@ static int tma_stencil_launch(TmaStencilState* st, int shape, const pf_config& c
 
 // Launch over the tile rows [ty0, ty1) with the next tick's deposits riding along: CTA = deposit tile
 // (kDepRows rows x kTmaCols columns x one channel), ring shape 4 x 4. The caller has checked
-// W % 4 == 0, W >= 128, stencil != 0; the rows are interior ones on a strip (no peer stores).
-static int tma_stencil_launch_dep(TmaStencilState* st, const PFDev& d, StencilArgs a, int ty0, int ty1,
+// W % 4 == 0, W >= 128, stencil != 0. with_peer: the launch contains the strip's first / last row and
+// neighbours are attached (pf_strip_tick steps the whole strip in this one launch: the tiles of the edge bands
+// simply have no passengers).
+static int tma_stencil_launch_dep(TmaStencilState* st, const PFDev& d, StencilArgs a, int ty0, int ty1, bool with_peer,
                                   cudaStream_t s) {
   a.r_begin = ty0 * kDepRows;
   a.r_end = ty1 * kDepRows < d.rows ? ty1 * kDepRows : d.rows;
   a.rows_per_cta = kDepRows;
   a.dep_ty0 = ty0;
   a.dep_ny = (d.rows + kDepRows - 1) / kDepRows;
-  a.peer.up = nullptr;
-  a.peer.dn = nullptr;
+  const bool peer = with_peer && ((a.peer.up && a.r_begin == 0) || (a.peer.dn && a.r_end == a.rows));
+  if (!peer) {
+    a.peer.up = nullptr;
+    a.peer.dn = nullptr;
+  }
   dim3 grid((d.W + kTmaCols - 1) / kTmaCols, ty1 - ty0, d.C);
+  if (peer) {
+    if (d.stencil == 5) return tma_launch_one<5, 4, 4, true, true>(st, 7, a, grid, s);
+    return tma_launch_one<9, 4, 4, true, true>(st, 7, a, grid, s);
+  }
   if (d.stencil == 5) return tma_launch_one<5, 4, 4, false, true>(st, 8, a, grid, s);
   return tma_launch_one<9, 4, 4, false, true>(st, 8, a, grid, s);
 }

@@ -92,6 +92,7 @@ struct pf_handle {
   unsigned long long peer_timeout_ns;
   int strip_dep0, strip_dep1;  // pf_strip_tick: rows handed over this tick (phase A decides, B and C use)
   bool strip_active;
+  bool strip_one_launch;      // set while pf_strip_tick drives the strip (see strip_tile_range)
   // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
   cudaEvent_t* strip_ev;
   int strip_used, strip_mark;
@@ -582,7 +583,11 @@ static PeerRows peer_rows(const pf_handle* h, int k) {
   return r;
 }
 
-static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, bool with_deposits = false) {
+// with_deposits: the next tick's deposits ride along (the lists of the tile rows tile_ty0..ty1 are ready).
+// whole_strip (with_deposits only): the launch covers every tile row of the strip, edge rows with their peer
+// stores included — the tiles outside tile_ty0..ty1 have empty lists.
+static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, bool with_deposits = false,
+                          bool whole_strip = false) {
   if (r_begin >= r_end) return PF_OK;
   const PFDev& d = h->dev;
   StencilArgs a;
@@ -600,7 +605,9 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, 
   if (with_deposits) {  // tile_ok() / strip_tile_range() hold: whole tile rows, TMA ring, CTA = deposit tile
     a.dep_flag = h->tile_flag; a.dep_count = h->tile_count; a.dep_blk = h->tile_blk;
     a.dep_dense = h->tile_dense; a.dep_side = h->tile_side;
-    int rc = tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, h->tile_ty1, s);
+    const int ny = (d.rows + kTileRows - 1) / kTileRows;
+    int rc = whole_strip ? tma_stencil_launch_dep(&h->tma, d, a, 0, ny, true, s)
+                         : tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, h->tile_ty1, false, s);
     if (rc != PF_OK) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
     h->launches++;
     return PF_OK;
@@ -766,7 +773,11 @@ static bool strip_tile_range(const pf_handle* h, const pf_agents* a, int* ty0, i
   const double step_cells = omega * h->cfg.wheel_radius * h->cfg.dt / h->cfg.cell_size;
   if (!(step_cells < 32.0)) return false;
   const int rows = h->dev.rows, ny = (rows + kTileRows - 1) / kTileRows;
-  int lo = ny / 8 > 1 ? ny / 8 : 1;
+  // pf_strip_tick steps the whole strip in one launch behind the move kernel: only the first tile row (and the
+  // last 64+ rows next to a neighbour) stay with the separate deposit. The phase-by-phase drivers step an eighth
+  // of the strip before the move kernel (to hide the halo exchange) and cannot hand those rows over.
+  int lo = (h->strip_one_launch || ny / 8 < 1) ? 1 : ny / 8;
+  if (h->cfg.row0 == 0 && h->strip_one_launch) lo = 0;  // the arena's top edge: no neighbour, no arrivals
   int hi = (h->cfg.row1 < h->cfg.H) ? (rows - kTileRows) / kTileRows : ny;
   if (hi <= lo) return false;
   *ty0 = lo;
@@ -1600,6 +1611,7 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       h->strip_mark = 0;
     }
     STRIP_MARK();  // 0: start
+    h->strip_one_launch = true;
     h->strip_dep0 = h->strip_dep1 = 0;
     if ((flags & PF_STEP_HANDOVER) && dep && move && (flags & PF_STEP_SENSE) && a->n > 0) {
       int ty0, ty1;
@@ -1614,13 +1626,17 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     if (rc) return rc;
     h->strip_active = true;
   }
-  const int lo = 1, hi = rows - 1 > 1 ? rows - 1 : 1;
   const bool handing = h->strip_dep1 > h->strip_dep0;
-  const int mid = handing ? h->strip_dep0 : lo + (hi - lo) / 2;
-  if (phases & PF_TICK_B) {  // interior rows while the halo is in flight, halo wait, agents, leavers out
+  // Without a hand-over the interior rows run while the halo is in flight (their launch costs nothing extra:
+  // the rest follows as one more launch). With it the whole strip is ONE launch behind the move kernel — a
+  // strip of 4096 rows split into four launches ran at 0.77 of the copy rate, against 0.99 in one piece
+  // (profiles/r02_notes.md) — and the halo wait (a flag that is almost always there already) is exposed.
+  const int lo = 1, hi = rows - 1 > 1 ? rows - 1 : 1;
+  const int mid = handing ? lo : lo + (hi - lo) / 2;
+  if (phases & PF_TICK_B) {  // halo wait, agents, leavers out
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase B without phase A");
     if (mid > lo) { rc = launch_stencil(h, lo, mid, s); if (rc) return rc; }
-    STRIP_MARK();  // 2: signal + stencil over the first rows
+    STRIP_MARK();  // 2: signal (+ stencil over the first rows when nothing is handed over)
     rc = pf_peer_wait(h, stream);
     if (rc) return rc;
     STRIP_MARK();  // 3: halo wait + ghost rows
@@ -1634,24 +1650,22 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     if (move) { rc = strip_pack(h, a, s); if (rc) return rc; }
     STRIP_MARK();  // 5: pack + migration signal
   }
-  if (phases & PF_TICK_C) {  // the remaining rows (deposits riding along), swap, arrivals in
+  if (phases & PF_TICK_C) {  // the field step (handed deposits ride along), swap, arrivals in
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase C without phase A");
-    bool last_done = false;
-    if (handing) {
-      rc = pf_step_field_rows(h, h->strip_dep0, h->strip_dep1, stream);  // exactly these rows: the deposits ride along
+    if (handing) {  // every row of the strip, edge rows and their peer stores included, in one launch
+      rc = launch_stencil(h, 0, rows, s, true, true);
       if (rc) return rc;
-      last_done = true;
-      if (h->strip_dep1 < rows) { rc = launch_stencil(h, h->strip_dep1, rows, s); if (rc) return rc; }
-    } else if (hi > mid) {
-      rc = launch_stencil(h, mid, hi, s);
+      h->tile_pending = false;
+      h->tile_handed = true;
+    } else {
+      if (hi > mid) { rc = launch_stencil(h, mid, hi, s); if (rc) return rc; }
+      rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
       if (rc) return rc;
+      if (rows > 1) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
     }
-    rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
-    if (rc) return rc;
-    if (rows > 1 && !last_done) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
     rc = pf_swap(h);
     if (rc) return rc;
-    STRIP_MARK();  // 6: stencil over the remaining rows
+    STRIP_MARK();  // 6: stencil
     if (move && (h->peer_up.set || h->peer_dn.set)) {
       k_peer_wait<<<1, 1, 0, s>>>(h->peer_up.set ? h->peer_flags + 2 : nullptr, h->peer_dn.set ? h->peer_flags + 3 : nullptr,
                                   h->mig_epoch, h->peer_timeout_ns, h->counters);
@@ -1667,6 +1681,7 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       h->strip_used++;
     }
     h->strip_active = false;
+    h->strip_one_launch = false;
     h->strip_dep0 = h->strip_dep1 = 0;
   }
   return PF_OK;
