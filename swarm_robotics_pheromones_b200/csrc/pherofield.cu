@@ -92,7 +92,8 @@ struct pf_handle {
   unsigned long long peer_timeout_ns;
   int strip_dep0, strip_dep1;  // pf_strip_tick: rows handed over this tick (phase A decides, B and C use)
   bool strip_active;
-  bool strip_one_launch;      // set while pf_strip_tick drives the strip (see strip_tile_range)
+  bool strip_one_launch;      // set while pf_strip_tick drives the strip in one-launch mode (see strip_tile_range)
+  bool strip_one_launch_opt;  // PF_OPT_STRIP_ONE_LAUNCH
   // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
   cudaEvent_t* strip_ev;
   int strip_used, strip_mark;
@@ -704,6 +705,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_NO_TILE_DEPOSIT) { h->no_tile_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_OWNER_DEPOSIT) { h->no_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_FORCE_OWNER_DEPOSIT) { h->force_owner_deposit = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value != 0; return PF_OK; }
   if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
@@ -1611,7 +1613,7 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       h->strip_mark = 0;
     }
     STRIP_MARK();  // 0: start
-    h->strip_one_launch = true;
+    h->strip_one_launch = h->strip_one_launch_opt;
     h->strip_dep0 = h->strip_dep1 = 0;
     if ((flags & PF_STEP_HANDOVER) && dep && move && (flags & PF_STEP_SENSE) && a->n > 0) {
       int ty0, ty1;
@@ -1627,16 +1629,18 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     h->strip_active = true;
   }
   const bool handing = h->strip_dep1 > h->strip_dep0;
-  // Without a hand-over the interior rows run while the halo is in flight (their launch costs nothing extra:
-  // the rest follows as one more launch). With it the whole strip is ONE launch behind the move kernel — a
-  // strip of 4096 rows split into four launches ran at 0.77 of the copy rate, against 0.99 in one piece
-  // (profiles/r02_notes.md) — and the halo wait (a flag that is almost always there already) is exposed.
+  const bool one_launch = handing && h->strip_one_launch;
+  // Default: the rows above the handed ones run while the halo is in flight (part A), the handed rows with their
+  // passengers and the band below follow behind the move kernel. PF_OPT_STRIP_ONE_LAUNCH steps the whole strip in ONE
+  // launch behind the move kernel instead (edge rows and their peer stores included; only the first tile row stays
+  // with the separate deposit): measured at 8 x 4096 rows it is 3 % slower (0.439 against 0.427 ms of stencil per
+  // tick, and the halo wait is exposed), profiles/r02_notes.md.
   const int lo = 1, hi = rows - 1 > 1 ? rows - 1 : 1;
-  const int mid = handing ? lo : lo + (hi - lo) / 2;
-  if (phases & PF_TICK_B) {  // halo wait, agents, leavers out
+  const int mid = one_launch ? lo : (handing ? h->strip_dep0 : lo + (hi - lo) / 2);
+  if (phases & PF_TICK_B) {  // interior rows while the halo is in flight, halo wait, agents, leavers out
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase B without phase A");
     if (mid > lo) { rc = launch_stencil(h, lo, mid, s); if (rc) return rc; }
-    STRIP_MARK();  // 2: signal (+ stencil over the first rows when nothing is handed over)
+    STRIP_MARK();  // 2: signal + stencil over the first rows
     rc = pf_peer_wait(h, stream);
     if (rc) return rc;
     STRIP_MARK();  // 3: halo wait + ghost rows
@@ -1650,18 +1654,27 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     if (move) { rc = strip_pack(h, a, s); if (rc) return rc; }
     STRIP_MARK();  // 5: pack + migration signal
   }
-  if (phases & PF_TICK_C) {  // the field step (handed deposits ride along), swap, arrivals in
+  if (phases & PF_TICK_C) {  // the remaining rows (handed deposits ride along), swap, arrivals in
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase C without phase A");
-    if (handing) {  // every row of the strip, edge rows and their peer stores included, in one launch
+    if (one_launch) {  // every row of the strip, edge rows and their peer stores included, in one launch
       rc = launch_stencil(h, 0, rows, s, true, true);
       if (rc) return rc;
       h->tile_pending = false;
       h->tile_handed = true;
     } else {
-      if (hi > mid) { rc = launch_stencil(h, mid, hi, s); if (rc) return rc; }
+      bool last_done = false;
+      if (handing) {
+        rc = pf_step_field_rows(h, h->strip_dep0, h->strip_dep1, stream);  // exactly these rows: the deposits ride along
+        if (rc) return rc;
+        last_done = true;
+        if (h->strip_dep1 < rows) { rc = launch_stencil(h, h->strip_dep1, rows, s); if (rc) return rc; }
+      } else if (hi > mid) {
+        rc = launch_stencil(h, mid, hi, s);
+        if (rc) return rc;
+      }
       rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
       if (rc) return rc;
-      if (rows > 1) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
+      if (rows > 1 && !last_done) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
     }
     rc = pf_swap(h);
     if (rc) return rc;

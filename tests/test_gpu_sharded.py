@@ -52,7 +52,7 @@ def test_strips_equal_unsharded_bitexact(world, variant, peer):
         w.b.field.close()
 
 
-@pytest.mark.parametrize("peer", [False, True])
+@pytest.mark.parametrize("peer", [False, True, "one-launch"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
     # strips tall enough to have interior tile rows (64 rows x 1024 columns): the move kernel hands the
@@ -70,6 +70,8 @@ def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
         strip = sharded.CudaStrip(sharded.strip_config(cfg, world, r), p["x"], p["y"], p["theta"],
                                   p["state"], p["gid"], capacity=14000, migrate_cap=1024)
         strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)  # 4-7 k robots per strip: below the default threshold
+        if peer == "one-launch":  # the whole strip in one stencil launch behind the move kernel (PF_OPT_STRIP_ONE_LAUNCH)
+            strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, 1)
         workers.append(sharded.StripWorker(strip, r, world))
     drv = sharded.LocalDriver(workers)
     if peer:
