@@ -463,6 +463,8 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
                                    stencil runs; falls back on the device when a tile is too crowded) */
 #define PF_OPT_STRIP_ONE_LAUNCH 8 /* pf_strip_tick: step the whole strip in one stencil launch behind the move kernel
                                     (default off: rows above the handed ones run while the halo is in flight) */
+#define PF_OPT_STRIP_PART_A_TILES 9 /* strips: tile rows (64 rows each) stepped before the move kernel while the halo is
+                                      in flight = the rows that cannot hand their deposits over; 0 = an eighth of the strip */
 #define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */

@@ -94,6 +94,7 @@ struct pf_handle {
   bool strip_active;
   bool strip_one_launch;      // set while pf_strip_tick drives the strip in one-launch mode (see strip_tile_range)
   bool strip_one_launch_opt;  // PF_OPT_STRIP_ONE_LAUNCH
+  int strip_part_a_tiles;     // PF_OPT_STRIP_PART_A_TILES (0 = an eighth of the strip)
   // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
   cudaEvent_t* strip_ev;
   int strip_used, strip_mark;
@@ -705,6 +706,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_NO_TILE_DEPOSIT) { h->no_tile_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_NO_OWNER_DEPOSIT) { h->no_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_FORCE_OWNER_DEPOSIT) { h->force_owner_deposit = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_STRIP_PART_A_TILES) { h->strip_part_a_tiles = value > 0 ? value : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value != 0; return PF_OK; }
   if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
@@ -779,6 +781,7 @@ static bool strip_tile_range(const pf_handle* h, const pf_agents* a, int* ty0, i
   // last 64+ rows next to a neighbour) stay with the separate deposit. The phase-by-phase drivers step an eighth
   // of the strip before the move kernel (to hide the halo exchange) and cannot hand those rows over.
   int lo = (h->strip_one_launch || ny / 8 < 1) ? 1 : ny / 8;
+  if (h->strip_part_a_tiles > 0) lo = h->strip_part_a_tiles < ny ? h->strip_part_a_tiles : ny;  // PF_OPT_STRIP_PART_A_TILES
   if (h->cfg.row0 == 0 && h->strip_one_launch) lo = 0;  // the arena's top edge: no neighbour, no arrivals
   int hi = (h->cfg.row1 < h->cfg.H) ? (rows - kTileRows) / kTileRows : ny;
   if (hi <= lo) return false;
