@@ -366,8 +366,8 @@ int pf_launch_count(const pf_handle* h, uint64_t* n);
 
 /* Row strips: deposits riding on the stencil (what pf_step does by itself on one GPU).
  * [row_begin, row_end) = the local rows whose next-tick deposits the stencil can apply, empty when the
- * feature is off for this handle (not a strip, no pf_agents_sort yet, stencil variant, ...). They never include
- * the first 64 rows nor the last 64 next to a neighbour. Protocol per tick, driven by the host:
+ * feature is off for this handle (not a strip, no pf_agents_sort yet, stencil variant, amounts that are not small
+ * integers, ...). They never include the first 64 rows nor the last 64 next to a neighbour. Protocol per tick, driven by the host:
  *   pf_agents_deposit            (skips the robots whose deposit the previous tick's stencil applied)
  *   pf_step_field_rows(1, row_begin)                       before the move kernel, as before
  *   pf_agents_step(flags | PF_STEP_HANDOVER)               bins + groups the interior rows' deposits
@@ -464,7 +464,7 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
 #define PF_OPT_STRIP_ONE_LAUNCH 8 /* pf_strip_tick: step the whole strip in one stencil launch behind the move kernel
                                     (default off: rows above the handed ones run while the halo is in flight) */
 #define PF_OPT_STRIP_PART_A_TILES 9 /* strips: tile rows (64 rows each) stepped before the move kernel while the halo is
-                                      in flight = the rows that cannot hand their deposits over; 0 = an eighth of the strip */
+                                      in flight = the rows that cannot hand their deposits over; 0 = one tile row */
 #define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */
