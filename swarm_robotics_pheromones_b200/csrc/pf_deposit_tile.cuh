@@ -223,8 +223,10 @@ k_tile_group(uint32_t* __restrict__ bcnt, const uint32_t* __restrict__ brec, uin
         }
       } else {
         tcount[tile] = total;
-        // getting close to the list's capacity: dense from the next tick on, without a fall-back in between
-        if (dense && total > (uint32_t)(kTileEnt * 3 / 4) && atomicCAS(dense + tile, -1, -2) == -1) {
+        // about to outgrow the list: dense from the next tick on, without a fall-back in between. (The margin is
+        // small on purpose: a tile of the uniform configs holds 1024 +- 32 cells, and a dense tile costs the move
+        // kernel an atomic per robot and the stencil CTA a second read stream.)
+        if (dense && total > (uint32_t)(kTileEnt - kTileEnt / 16) && atomicCAS(dense + tile, -1, -2) == -1) {
           const uint32_t slot = atomicAdd(pool, 1u);
           dense[tile] = slot < (uint32_t)pool_cap ? (int)slot : -1;
         }
