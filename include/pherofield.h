@@ -386,11 +386,6 @@ int pf_tile_stats(pf_handle* h, uint64_t* attempted, uint64_t* fell_back);
  * per-tile lists (more than one robot per few cells, e.g. a nest) and go through a per-cell side buffer instead, and
  * the number of such buffers available. Synchronises the device. */
 int pf_tile_dense(pf_handle* h, uint64_t* n_dense, uint64_t* pool_slots);
-/* Sense riding on the stencil ("pre-sense", PF_OPT_PRESENSE): robot-ticks whose five sensed values (sense_pheromone,
- * sup:379-417) and ordered arg-max (sup:440-450) were taken out of L2 by the stencil CTA that had just written the
- * cells, instead of being gathered from HBM by the move kernel. Same cells, same values, same comparison: the
- * decisions are identical either way. Since pf_create / pf_counters_reset. Synchronises the device. */
-int pf_presense_stats(pf_handle* h, uint64_t* served);
 
 /* Per-phase device times of pf_step, from CUDA events recorded on the launching streams while
  * profiling is enabled (bench.py's live roofline numbers). Times are sums over `ticks` ticks. */
@@ -470,10 +465,6 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
                                     (default off: rows above the handed ones run while the halo is in flight) */
 #define PF_OPT_STRIP_PART_A_TILES 9 /* strips: tile rows (64 rows each) stepped before the move kernel while the halo is
                                       in flight = the rows that cannot hand their deposits over; 0 = one tile row */
-#define PF_OPT_PRESENSE 10 /* pf_step: the stencil CTA that writes a tile also senses for the robots that will stand on it
-                             next tick (five L2 loads + arg-max, one byte per robot), so the next move kernel does not
-                             gather from HBM. 0 = off, 1 = on, -1 = auto (default: on where ticks are not replayed from
-                             a CUDA graph, i.e. fields that do not live in L2) */
 #define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */

@@ -61,7 +61,6 @@ SIGNATURES = {
     "pf_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "pf_tile_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pf_tile_dense": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "pf_presense_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "pf_tile_rows": (C.c_int, [_vp, _agp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pf_profile_enable": (C.c_int, [_vp, C.c_int]),
     "pf_profile_read": (C.c_int, [_vp, C.POINTER(abi.PFProfile), C.c_int]),

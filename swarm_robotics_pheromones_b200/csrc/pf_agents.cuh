@@ -168,24 +168,27 @@ __device__ __forceinline__ int pf_nearest_food(const PFDev& p, float x, float y,
   return best;
 }
 
-// the five DRUL cells (reference sup:379-417 in dict order sup:390); inside[d] = direction present
-__device__ __forceinline__ void pf_sense_cells(const PFDev& p, float x, float y, float theta, int r[5], int q[5],
-                                               bool inside[5]) {
+// the five DRUL values (reference sup:379-417 in dict order sup:390); NaN = direction absent
+__device__ __forceinline__ void pf_sense5(const PFDev& p, const float* __restrict__ f, float x,
+                                          float y, float theta, uint32_t st, float v[5]) {
+  const int ch = p.sen_ch[st & 3u];
   float s = 0.0f, co = 1.0f;
   if (p.sense_mode == PF_SENSE_HEADING) pf_sincos(theta, s, co);
   int r0, q0;
   pf_cell(p, x, y, r0, q0);
 #pragma unroll
   for (int d = 0; d < 5; ++d) {
+    int r, q;
+    bool inside;
     if (p.sense_mode == PF_SENSE_WORLD) {
-      r[d] = r0 + p.drow[d];
-      q[d] = q0 + p.dcol[d];
-      inside[d] = (r[d] >= 0 && r[d] < p.H && q[d] >= 0 && q[d] < p.W);
-      if (d == PF_DIR_CURRENT) inside[d] = true;
+      r = r0 + p.drow[d];
+      q = q0 + p.dcol[d];
+      inside = (r >= 0 && r < p.H && q >= 0 && q < p.W);
+      if (d == PF_DIR_CURRENT) inside = true;
     } else if (d == PF_DIR_CURRENT) {
-      r[d] = r0;
-      q[d] = q0;
-      inside[d] = true;
+      r = r0;
+      q = q0;
+      inside = true;
     } else {
       float ux, uy;
       if (d == PF_DIR_FRONT) { ux = co; uy = s; }
@@ -194,25 +197,27 @@ __device__ __forceinline__ void pf_sense_cells(const PFDev& p, float x, float y,
       else { ux = s; uy = -co; }
       float px = fadd(x, fmul(p.sense_dist, ux));
       float py = fadd(y, fmul(p.sense_dist, uy));
-      inside[d] = pf_cell(p, px, py, r[d], q[d]);
+      inside = pf_cell(p, px, py, r, q);
     }
-  }
-}
-
-// the five DRUL values; NaN = direction absent
-__device__ __forceinline__ void pf_sense5(const PFDev& p, const float* __restrict__ f, float x,
-                                          float y, float theta, uint32_t st, float v[5]) {
-  const int ch = p.sen_ch[st & 3u];
-  int r[5], q[5];
-  bool inside[5];
-  pf_sense_cells(p, x, y, theta, r, q, inside);
-#pragma unroll
-  for (int d = 0; d < 5; ++d) {
-    if (inside[d] && r[d] >= p.row0 - 1 && r[d] <= p.row1)
-      v[d] = __ldg(f + pf_addr(p, ch, r[d], q[d]));
+    if (inside && r >= p.row0 - 1 && r <= p.row1)
+      v[d] = __ldg(f + pf_addr(p, ch, r, q));
     else
       v[d] = __int_as_float(0x7fc00000);
   }
+}
+
+__device__ __forceinline__ int pf_argmax5(const float v[5]) {
+  int dir = -1;
+  float best = 0.0f;
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    if (v[d] != v[d]) continue;
+    if (dir < 0 || v[d] > best) {
+      best = v[d];
+      dir = d;
+    }
+  }
+  return dir;
 }
 
 __global__ void __launch_bounds__(256)
@@ -237,22 +242,15 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
               uint8_t* __restrict__ dec_out, unsigned long long* __restrict__ counters,
               uint32_t* __restrict__ mig_cnt, uint32_t* __restrict__ next_keys,
               float* __restrict__ next_vals, uint32_t sentinel, uint32_t* __restrict__ cmin,
-              uint32_t* __restrict__ cmax, TileBins tb, uint8_t* __restrict__ sdir, SenseBins sb) {
-  // sdir (may be null): per robot, the direction the last stencil launch sensed for it (pf_deposit_tile.cuh,
-  // "pre-sense"); consumed and cleared here. sb.cnt (may be null): requests for the next tick go to these bins.
-  __shared__ unsigned int hist[10];  // 0..5 decisions, 6 grabbed, 7 delivered, 8 deposits (next tick), 9 pre-sensed
-  if (threadIdx.x < 10) hist[threadIdx.x] = 0;
+              uint32_t* __restrict__ cmax, TileBins tb) {
+  __shared__ unsigned int hist[9];  // 0..5 decisions, 6 grabbed, 7 delivered, 8 deposits (next tick)
+  if (threadIdx.x < 9) hist[threadIdx.x] = 0;
   __syncthreads();
   // grid-stride over a fixed grid: the decision histogram is flushed once per CTA
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     uint32_t mt = ameta[i];
     uint32_t st = mt & PF_META_STATE_MASK;
-    uint32_t pre = 0u;
-    if (sdir) {
-      pre = sdir[i];
-      if (pre) sdir[i] = 0;
-    }
     if (st == PF_STATE_EMPTY) {
       if (dec_out) dec_out[i] = PF_DEC_NONE;
       if (next_keys) { next_keys[i] = sentinel; next_vals[i] = 0.0f; }
@@ -267,15 +265,9 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
         wl = p.bl;  // Braitenberg base speeds only (reference sup:721-725, 736-744)
         wr = p.br;
       } else if (st == PF_STATE_SEARCHING) {
-        int dir;
-        if (pre & kSenseValid) {  // sensed by the stencil CTA that wrote the cells
-          dir = (int)(pre & 7u) - 1;
-          atomicAdd(&hist[9], 1u);
-        } else {
-          float v5[5];
-          pf_sense5(p, f, x, y, th, st, v5);
-          dir = pf_argmax5(v5);
-        }
+        float v5[5];
+        pf_sense5(p, f, x, y, th, st, v5);
+        int dir = pf_argmax5(v5);
         float d2;
         int k = pf_nearest_food(p, x, y, d2);
         float turn = pf_pid_turn(p, x, y, p.food_x[k], p.food_y[k]);
@@ -433,31 +425,6 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
       }
       ameta[i] = nm;
       if (dec_out) dec_out[i] = (uint8_t)dec;
-      if (sb.cnt) {  // what this robot will sense next tick, asked of the stencil tile that holds all five cells
-        int stile = -1;
-        uint32_t packed = 0u;
-        if (st == PF_STATE_SEARCHING) {
-          int r5[5], q5[5];
-          bool in5[5];
-          pf_sense_cells(p, x, y, th, r5, q5, in5);
-          const int lr = r5[0] - p.row0, col = q5[0];
-          const int tr = lr & (kTileRows - 1), tc = col & (kTileCols - 1);
-          bool ok = lr >= 0 && lr + 1 < p.rows && tr >= 1 && tr <= kTileRows - 2 && col + 1 < p.W && tc >= 1 &&
-                    tc <= kTileCols - 2;
-          uint32_t codes = 0u;
-#pragma unroll
-          for (int d = 1; d < 5; ++d) {
-            const int dr = r5[d] - r5[0], dq = q5[d] - q5[0];
-            ok = ok && in5[d] && dr >= -1 && dr <= 1 && dq >= -1 && dq <= 1;
-            codes |= sense_code(dr, dq) << (4 * (d - 1));
-          }
-          if (ok) {
-            stile = (p.sen_ch[PF_STATE_SEARCHING] * sb.ny + lr / kTileRows) * sb.nx + col / kTileCols;
-            packed = (uint32_t)(tr * kTileCols + tc) | (codes << 16);
-          }
-        }
-        sense_bin_put(sb, __activemask(), stile, (uint32_t)i, packed);
-      }
       if (mig_cnt) {  // same rule as mig_leaves: did the (new) cell row leave the strip? (rare: one atomic each)
         int r, q;
         pf_cell(p, x, y, r, q);
@@ -470,7 +437,6 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
   if (threadIdx.x < 8 && hist[threadIdx.x])
     atomicAdd(&counters[2 + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
   if (threadIdx.x == 8 && hist[8]) atomicAdd(&counters[1], (unsigned long long)hist[8]);
-  if (threadIdx.x == 9 && hist[9]) atomicAdd(&counters[14], (unsigned long long)hist[9]);
 }
 
 // storingPosition + has_moved (reference sup:279-289, 260-273) for externally measured poses

@@ -127,56 +127,6 @@ __device__ __forceinline__ int tile_of(const TileBins& tb, int ch, int lr, int c
   return ((ch * tb.ny + ty) * tb.nx + tx) * kTileGroups + (r + 2) / kTileStageRows;
 }
 
-// ------------------------------------------------------------------------------------------
-// Sense riding on the stencil ("pre-sense"): the NEXT tick's five sensed values are read by the
-// stencil CTA that has just written them, out of L2, instead of being gathered from HBM by the next
-// move kernel (three 64 B DRAM atoms per robot for five 4 B values: 3.7 GB of reads per tick at
-// config 3, 4.7 x the algorithmic bytes — profiles/r02_kernels_c3.md).
-//
-//   move kernel   after moving a robot that will sense next tick (SEARCHING: sup:581-588), works out the
-//                 five cells it will sense (same code as the gather path) and, if all of them lie inside
-//                 the stencil tile of its centre cell (centre not on the tile's border rows / columns:
-//                 96.7 % of a uniform population), drops ONE 8-byte request into the tile's sense bin:
-//                 robot index, centre cell within the tile, four 4-bit neighbour codes;
-//   k_stencil_tma<.., DEP>  once the tile is stored and its deposits are applied, all warps of the CTA serve
-//                 the requests: five L2 loads, the reference's ordered arg-max (sup:440-450), one byte per
-//                 robot (0x80 | direction + 1) into sense_dir[robot];
-//   next move kernel   reads that byte (and clears it): valid -> the direction is known, no gather;
-//                 not valid (border cell, bin overflow, a tick whose deposits fell back) -> gathers as before.
-//
-// Exact by construction: the values compared are the cells' final fp32 values of that tick (stencil output
-// + the next tick's deposits, which the same CTA applied before), the comparison is the same function.
-// A byte is only ever consumed by the move kernel that directly follows the stencil that wrote it (it is
-// cleared on read and at the start of every pf_step call), so no epoch is needed.
-constexpr int kSenseCap = 1280;  // requests per tile; a uniform tile of config 3 holds 990 +- 32
-constexpr uint32_t kSenseValid = 0x80u;
-static_assert((kTileRows & (kTileRows - 1)) == 0 && (kTileCols & (kTileCols - 1)) == 0 && kTileRows * kTileCols <= 65536,
-              "centre cell within the tile: 16 bits, masks");
-
-struct SenseBins {
-  uint32_t* cnt;   // [tile] requests in the bin (cleared before the move kernel); null: no requests
-  uint2* req;      // [tile * kSenseCap + k]: x = robot index, y = centre cell | codes << 16
-  int nx, ny;      // tiles along a row / along a column of one channel plane (as TileBins)
-};
-
-// code of a neighbour cell (dr, dq in -1..1) relative to the centre
-__device__ __forceinline__ uint32_t sense_code(int dr, int dq) { return (uint32_t)((dr + 1) * 3 + (dq + 1)); }
-
-// Called by every thread of `act` (converged); tile < 0 = no request. One counter update per (warp, tile).
-__device__ __forceinline__ void sense_bin_put(const SenseBins& sb, unsigned act, int tile, uint32_t robot, uint32_t packed) {
-  const int lane = threadIdx.x & 31;
-  const unsigned peers = __match_any_sync(act, tile);
-  if (tile >= 0) {
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0u;
-    if (lane == leader) base = atomicAdd(sb.cnt + tile, (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    if (pos < (uint32_t)kSenseCap) sb.req[(long long)tile * kSenseCap + pos] = make_uint2(robot, packed);
-    // else: not served, the robot gathers next tick
-  }
-}
-
 // per tile: tcount = number of (cell, total) entries, block = start[] / cell[] / sum[] as laid out above
 constexpr int kGroupWarps = (kTileGroups + 1) / 2;  // 9: warp w takes stage groups 2w and 2w + 1
 constexpr int kGroupThreads = kGroupWarps * 32;

@@ -152,18 +152,3 @@ __device__ __forceinline__ bool pf_cell(const PFDev& p, float x, float y, int& r
 __device__ __forceinline__ long long pf_addr(const PFDev& p, int ch, int grow, int col) {
   return (long long)ch * p.chan_stride + (long long)(grow - p.row0 + 1) * p.pitch + col;
 }
-
-// ordered arg-max over the present directions, strict '>' (reference sup:440-450); NaN = absent, -1 = none
-__device__ __forceinline__ int pf_argmax5(const float v[5]) {
-  int dir = -1;
-  float best = 0.0f;
-#pragma unroll
-  for (int d = 0; d < 5; ++d) {
-    if (v[d] != v[d]) continue;
-    if (dir < 0 || v[d] > best) {
-      best = v[d];
-      dir = d;
-    }
-  }
-  return dir;
-}

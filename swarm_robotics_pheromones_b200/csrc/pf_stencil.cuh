@@ -35,10 +35,6 @@ struct StencilArgs {
   int dep_ty0, dep_ny;           // tile row of this launch's first CTA row; tile rows per channel
   const int* dep_dense;          // [tile] side buffer slot of a crowded tile, < 0 = none (pf_deposit_tile.cuh)
   float* dep_side;               // [slot][64 * 1024] per-cell totals: added to the output rows, then cleared
-  // next tick's sense requests, served out of L2 by the CTA that wrote the cells (pf_deposit_tile.cuh, "pre-sense")
-  const uint32_t* sn_cnt;        // [tile] requests; null: none
-  const uint2* sn_req;           // [tile * 1280] robot index, centre cell | neighbour codes << 16
-  uint8_t* sn_dir;               // [robot] 0x80 | arg-max direction + 1
 };
 
 // per-channel constant without dynamic indexing of the kernel parameter block (which would make

@@ -21,7 +21,6 @@ constexpr int kDepEnt = 1408;   // = kTileEnt
 constexpr int kDepPtrBytes = 48;           // uint16 start[] of the per-stage entry groups (= kTilePtrBytes)
 constexpr int kDepColBytes = kDepEnt * 2;  // uint16 row << 10 | column
 constexpr int kDepBlkBytes = kDepPtrBytes + kDepColBytes + kDepEnt * 4;
-constexpr int kSnCap = 1280;    // sense requests per tile (= kSenseCap)
 
 struct TmaStencilState {
   bool attr_set[3][9];
@@ -107,10 +106,9 @@ k_stencil_tma(StencilArgs a) {
   long long tile = 0;
   float* side = nullptr;      // crowded tile: per-cell totals to add to the output (uniform per CTA)
   bool side_add = false;
-  bool usable = false;
   if (DEP) {
     tile = ((long long)ch * a.dep_ny + a.dep_ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
-    usable = *a.dep_flag == 0u;
+    const bool usable = *a.dep_flag == 0u;
     if (usable) ndep = a.dep_count[tile];  // uniform per CTA
     const int slot = a.dep_dense ? a.dep_dense[tile] : -1;
     if (slot >= 0) side = a.dep_side + (long long)slot * (kDepRows * kTmaCols);
@@ -185,9 +183,10 @@ k_stencil_tma(StencilArgs a) {
       }
       mbar_wait(fin, 0u);  // the last kStages + 1 stages, after the consumers' last stores
       dep_stages(max(niter - kStages - 1, 0), niter);
-      if (a.sn_cnt) __threadfence();  // the reductions are performed before the sense phase reads the cells
     }
-  } else {
+    return;
+  }
+
   // ===== consumers =====
   const int t = threadIdx.x;  // 0..255
   int col4 = c0 + 4 * t;
@@ -262,45 +261,6 @@ k_stencil_tma(StencilArgs a) {
   if (DEP && ndep) {
     __syncwarp();
     if (lane == 0) mbar_arrive(fin);
-  }
-  }  // consumers
-
-  // ===== sense phase ("pre-sense", pf_deposit_tile.cuh) =====
-  // The tile is stored and its deposits are applied: every warp of the CTA now serves the tile's sense
-  // requests for the NEXT tick out of L2 — five loads, the ordered arg-max, one byte per robot. Not on a tick
-  // whose deposits fell back (the cells do not hold them yet): those robots gather as before.
-  if (DEP && a.sn_cnt) {  // uniform per launch
-    __syncthreads();      // all stores and reductions of this CTA are behind this barrier
-    uint32_t nreq = usable ? a.sn_cnt[tile] : 0u;
-    if (nreq > (uint32_t)kSnCap) nreq = (uint32_t)kSnCap;
-    const uint2* __restrict__ rq = a.sn_req + tile * kSnCap;
-    const float* const tbase = a.nxt + ch * a.chan_stride + a.pitch + (long long)r0 * a.pitch + c0;
-    constexpr int kPer = (kSnCap + kTmaThreads - 1) / kTmaThreads;
-    uint2 rec[kPer];
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) {
-      const uint32_t k = threadIdx.x + (uint32_t)j * kTmaThreads;
-      rec[j] = k < nreq ? __ldcs(rq + k) : make_uint2(0xffffffffu, 0u);
-    }
-    float v[kPer][5];
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) {
-      if (rec[j].x == 0xffffffffu) continue;
-      const uint32_t cell = rec[j].y & 0xffffu;
-      const float* c = tbase + (long long)(cell >> 10) * a.pitch + (cell & 1023u);
-      v[j][0] = __ldcg(c);
-#pragma unroll
-      for (int d = 1; d < 5; ++d) {
-        const int code = (int)((rec[j].y >> (16 + 4 * (d - 1))) & 15u);
-        const int dr = code / 3 - 1, dq = code % 3 - 1;
-        v[j][d] = __ldcg(c + (long long)dr * a.pitch + dq);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) {
-      if (rec[j].x == 0xffffffffu) continue;
-      a.sn_dir[rec[j].x] = (uint8_t)(0x80u | (uint32_t)(pf_argmax5(v[j]) + 1));
-    }
   }
 }
 

@@ -72,13 +72,6 @@ struct pf_handle {
   bool tile_handed;       // strips: that launch has happened; the next pf_agents_deposit skips those agents
   uint32_t own_handed_lo, own_handed_hi;  // ... and the sort-free deposit kernel skips key ranges inside these cells
   int tile_ty0, tile_ty1; // tile rows handed over
-  // sense riding on the stencil ("pre-sense", pf_deposit_tile.cuh): per-tile request bins, one byte per robot
-  uint32_t* sense_cnt;
-  uint2* sense_req;
-  uint8_t* sense_dir;
-  long long sense_dir_cap;
-  int presense;           // PF_OPT_PRESENSE: 0 off, 1 on, < 0 auto (on unless ticks are replayed from a CUDA graph)
-  bool sense_pending;     // the move kernel of this tick filled the bins: the stencil launch serves them
   unsigned long long tile_attempts, g_tile_attempts;
   long long own_alloc;      // chunks allocated
   long long own_n;          // agent slots the splitters were built for (0 = invalid)
@@ -162,12 +155,10 @@ static size_t mig_box_words(long long cap) { return (size_t)(cap + 1) * PF_MIGRA
 static void graph_drop(pf_handle* h);
 
 static void tile_free(pf_handle* h) {
-  void** arrs[11] = {(void**)&h->tile_bcnt, (void**)&h->tile_brec, (void**)&h->tile_flag, (void**)&h->tile_count,
-                     (void**)&h->tile_blk, (void**)&h->tile_pool, (void**)&h->tile_dense, (void**)&h->tile_side,
-                     (void**)&h->sense_cnt, (void**)&h->sense_req, (void**)&h->sense_dir};
+  void** arrs[8] = {(void**)&h->tile_bcnt, (void**)&h->tile_brec, (void**)&h->tile_flag, (void**)&h->tile_count,
+                    (void**)&h->tile_blk, (void**)&h->tile_pool, (void**)&h->tile_dense, (void**)&h->tile_side};
   for (auto pp : arrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   h->tile_alloc = 0;
-  h->sense_dir_cap = 0;
 }
 
 static inline unsigned blocks_for(long long n, int threads) {
@@ -385,7 +376,6 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
   h->rows_per_cta = 0;
   // launch-bound problems (field + agents small enough that a tick is a few tens of microseconds)
   h->use_graph = (h->buf_elems <= (1ll << 24)) ? 1 : 0;
-  h->presense = -1;
   tma_stencil_init(&h->tma);
   *out = h;
   return PF_OK;
@@ -614,11 +604,6 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, 
   a.peer = peer_rows(h, h->cur ^ 1);
   a.dep_flag = nullptr; a.dep_count = nullptr; a.dep_blk = nullptr; a.dep_ty0 = 0; a.dep_ny = 0;
   a.dep_dense = nullptr; a.dep_side = nullptr;
-  a.sn_cnt = nullptr; a.sn_req = nullptr; a.sn_dir = nullptr;
-  if (with_deposits && h->sense_pending) {
-    a.sn_cnt = h->sense_cnt; a.sn_req = h->sense_req; a.sn_dir = h->sense_dir;
-    h->sense_pending = false;
-  }
   if (with_deposits) {  // tile_ok() / strip_tile_range() hold: whole tile rows, TMA ring, CTA = deposit tile
     a.dep_flag = h->tile_flag; a.dep_count = h->tile_count; a.dep_blk = h->tile_blk;
     a.dep_dense = h->tile_dense; a.dep_side = h->tile_side;
@@ -724,7 +709,6 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_STRIP_PART_A_TILES) { h->strip_part_a_tiles = value > 0 ? value : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value != 0; return PF_OK; }
   if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
-  if (option == PF_OPT_PRESENSE) { h->presense = value < 0 ? -1 : (value ? 1 : 0); graph_drop(h); return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
 }
@@ -847,41 +831,6 @@ static int tile_begin(pf_handle* h, cudaStream_t s, TileBins* tb, int ty0, int t
   tb->flag = h->tile_flag; tb->nx = nx; tb->ny = ny; tb->ty_lo = ty0; tb->ty_hi = ty1;
   h->tile_ty0 = ty0;
   h->tile_ty1 = ty1;
-  return PF_OK;
-}
-
-// Pre-sense (pf_deposit_tile.cuh): on unless switched off; in auto mode not where ticks are replayed from a CUDA
-// graph (fields that live in L2: the gathers cost nothing there and the stencil CTAs would only get a longer tail).
-static bool presense_on(const pf_handle* h) { return h->presense > 0 || (h->presense < 0 && !h->use_graph); }
-
-// storage of the sense bins (tile_begin has run: tile_alloc tiles) and of the per-robot byte; bins cleared on `s`
-static int sense_begin(pf_handle* h, cudaStream_t s, SenseBins* sb) {
-  const long long ntiles = h->tile_alloc;
-  if (!h->sense_cnt) {
-    PF_CUDA(h, cudaMalloc(&h->sense_cnt, sizeof(uint32_t) * ntiles));
-    PF_CUDA(h, cudaMalloc(&h->sense_req, sizeof(uint2) * (size_t)ntiles * kSenseCap));
-  }
-  if (h->sense_dir_cap < h->cap) {
-    if (h->sense_dir) { PF_CUDA(h, cudaFree(h->sense_dir)); h->sense_dir = nullptr; }
-    PF_CUDA(h, cudaMalloc(&h->sense_dir, (size_t)h->cap));
-    PF_CUDA(h, cudaMemset(h->sense_dir, 0, (size_t)h->cap));
-    h->sense_dir_cap = h->cap;
-  }
-  PF_CUDA(h, cudaMemsetAsync(h->sense_cnt, 0, sizeof(uint32_t) * ntiles, s));
-  sb->cnt = h->sense_cnt;
-  sb->req = h->sense_req;
-  sb->nx = (h->dev.W + kTileCols - 1) / kTileCols;
-  sb->ny = (h->dev.rows + kTileRows - 1) / kTileRows;
-  return PF_OK;
-}
-
-extern "C" int pf_presense_stats(pf_handle* h, uint64_t* served) {
-  if (!h || !served) return PF_EINVAL;
-  PF_CUDA(h, cudaSetDevice(h->cfg.device));
-  unsigned long long v = 0;
-  PF_CUDA(h, cudaDeviceSynchronize());
-  PF_CUDA(h, cudaMemcpy(&v, h->counters + 14, sizeof(v), cudaMemcpyDeviceToHost));
-  *served = v;
   return PF_OK;
 }
 
@@ -1012,8 +961,7 @@ extern "C" int pf_sense(pf_handle* h, int64_t n, const float* x, const float* y,
 }
 
 static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, uint8_t* dec, cudaStream_t s,
-                              bool emit_next_keys = false, const TileBins* bins = nullptr, uint8_t* sdir = nullptr,
-                              const SenseBins* sense = nullptr) {
+                              bool emit_next_keys = false, const TileBins* bins = nullptr) {
   // on a strip, the move kernel also counts the leavers per chunk for pf_migrate_pack
   uint32_t* mig = nullptr;
   if (is_sharded(h) && (flags & PF_STEP_MOVE) && h->mig_cnt && a->n <= h->cap) {
@@ -1027,8 +975,6 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
   float* nv = nullptr;
   TileBins no_bins;
   memset(&no_bins, 0, sizeof(no_bins));
-  SenseBins no_sense;
-  memset(&no_sense, 0, sizeof(no_sense));
   if (emit_next_keys) {  // keys_in / vals_in of the sort scratch, for the next tick's deposit
     nk = (uint32_t*)h->scratch;
     nv = (float*)(nk + 2 * h->cap);
@@ -1038,7 +984,7 @@ static int launch_agents_step(pf_handle* h, const pf_agents* a, uint32_t flags, 
                                                      nk, nv, h->sentinel,
                                                      (nk && owner_ready(h, a)) ? h->own_cmin : nullptr,
                                                      (nk && owner_ready(h, a)) ? h->own_cmax : nullptr,
-                                                     bins ? *bins : no_bins, sdir, sense ? *sense : no_sense);
+                                                     bins ? *bins : no_bins);
   PF_LAUNCH_CHECK(h);
   return PF_OK;
 }
@@ -1151,12 +1097,9 @@ extern "C" int pf_step(pf_handle* h, const pf_agents* a, int nsteps, void* strea
 
 // One tick enqueued on `s`. keys_ready: the previous tick's move kernel already produced this tick's
 // deposit keys; emit_next: produce the next tick's keys in this tick's move kernel.
-// sense_ready (in/out): the previous tick's stencil served sense requests, this tick's move kernel reads them.
 static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream_t s, bool keys_ready,
-                     bool emit_next, bool* keys_ready_out, bool* sense_ready) {
+                     bool emit_next, bool* keys_ready_out) {
   int rc;
-  const bool sense_in = *sense_ready;  // only the move kernel directly behind the serving stencil may read the bytes
-  *sense_ready = false;
   const double now = h->t0 + (double)h->ticks * (double)h->cfg.dt;
   const bool sense = (now >= h->start_delay) && (mask & PF_STEP_SENSE);
   const uint32_t flags = (mask & PF_STEP_MOVE) | (sense ? PF_STEP_SENSE : 0u);
@@ -1197,22 +1140,12 @@ static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream
     // hand the next tick's deposits to this tick's stencil? (pf_deposit_tile.cuh)
     const bool tile_try = emit && (mask & PF_STEP_FIELD) && tile_ok(h, a);
     TileBins bins;
-    SenseBins sbins;
-    // ... and the next tick's sensing with them ("pre-sense"): only when that tick is certain to sense
-    const bool sense_try = tile_try && presense_on(h) && sense && (mask & PF_STEP_MOVE);
     if (tile_try) {
       rc = tile_begin(h, as, &bins, 0, (h->dev.rows + kTileRows - 1) / kTileRows);
       if (rc) return rc;
-      if (sense_try) {
-        rc = sense_begin(h, as, &sbins);
-        if (rc) return rc;
-      }
     }
-    rc = launch_agents_step(h, a, flags, nullptr, as, emit, tile_try ? &bins : nullptr,
-                            (sense_in && h->sense_dir_cap >= a->n) ? h->sense_dir : nullptr,
-                            sense_try ? &sbins : nullptr);
+    rc = launch_agents_step(h, a, flags, nullptr, as, emit, tile_try ? &bins : nullptr);
     if (rc) return rc;
-    h->sense_pending = sense_try;
     *keys_ready_out = emit;
     if (tile_try) {
       rc = tile_finish(h, as);
@@ -1225,11 +1158,9 @@ static int tick_once(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream
   }
   if (pe) PF_CUDA(h, cudaEventRecord(pe[5], s));
   if (mask & PF_STEP_FIELD) {
-    *sense_ready = h->tile_pending && h->sense_pending;
     rc = launch_stencil(h, 0, h->dev.rows, s, h->tile_pending);
     if (rc) return rc;
   }
-  h->sense_pending = false;
   if (pe) {
     PF_CUDA(h, cudaEventRecord(pe[2], s));
     h->prof_used++;
@@ -1250,13 +1181,12 @@ static void graph_drop(pf_handle* h) {
 }
 
 // Capture two steady-state ticks (the double buffer returns to its parity) into a CUDA graph.
-static int graph_prepare(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream_t s, bool* sense_ready) {
+static int graph_prepare(pf_handle* h, const pf_agents* a, uint32_t mask, cudaStream_t s) {
   GraphKey k;
   memset(&k, 0, sizeof(k));
   k.x = a->x; k.y = a->y; k.theta = a->theta; k.wl = a->wl; k.wr = a->wr; k.meta = a->meta;
   k.n = a->n; k.mask = mask; k.parity = h->cur; k.variant = h->variant; k.rpc = h->rows_per_cta;
-  k.tile = (h->tile_pending ? 1 : 0) | (tile_ok(h, a) ? 2 : 0) | (owner_ready(h, a) ? 4 : 0) |
-           (presense_on(h) ? 8 : 0) | (*sense_ready ? 16 : 0);
+  k.tile = (h->tile_pending ? 1 : 0) | (tile_ok(h, a) ? 2 : 0) | (owner_ready(h, a) ? 4 : 0);
   k.scratch = h->scratch; k.cap = h->cap;
   if (h->g_exec && memcmp(&k, &h->g_key, sizeof(k)) == 0) return PF_OK;
   graph_drop(h);
@@ -1268,12 +1198,8 @@ static int graph_prepare(pf_handle* h, const pf_agents* a, uint32_t mask, cudaSt
   cudaStream_t cs = h->side;
   PF_CUDA(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
   bool kr = true;
-  const bool sr0 = *sense_ready;
-  bool sr = sr0;
-  int rc = tick_once(h, a, mask, cs, true, true, &kr, &sr);
-  if (rc == PF_OK && sr != sr0) rc = set_err(h, PF_ESTATE, "graph capture: the tick is not in its steady state");
-  if (rc == PF_OK) rc = tick_once(h, a, mask, cs, kr, true, &kr, &sr);
-  if (rc == PF_OK && sr != sr0) rc = set_err(h, PF_ESTATE, "graph capture: the tick is not in its steady state");
+  int rc = tick_once(h, a, mask, cs, true, true, &kr);
+  if (rc == PF_OK) rc = tick_once(h, a, mask, cs, kr, true, &kr);
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(cs, &g);
   h->g_nodes = h->launches - launches0;
@@ -1301,12 +1227,8 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
   if (rc) return rc;
   PF_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  bool keys_ready = false, sense_ready = false;
+  bool keys_ready = false;
   h->tile_pending = false;
-  h->sense_pending = false;
-  // no byte of an earlier call survives into this one (every valid byte is cleared by the move kernel that reads
-  // it, and the last tick of a call asks for none): belt and braces, the poses may have been replaced since
-  if (h->sense_dir && presense_on(h)) PF_CUDA(h, cudaMemsetAsync(h->sense_dir, 0, (size_t)h->sense_dir_cap, s));
   int t = 0;
   // CUDA-graph path for launch-bound (small) problems: tick 0 normally (builds keys), then pairs of
   // steady-state ticks replayed from one graph, the last tick normally (must not pre-bump the
@@ -1315,12 +1237,12 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
   const bool graph_ok = h->use_graph && !h->prof_on && !h->overlap_agents && !h->no_fused_keys && a->n > 0 &&
                         nsteps >= 6 && mask == PF_STEP_ALL && now0 >= h->start_delay;
   if (graph_ok) {
-    rc = tick_once(h, a, mask, s, false, true, &keys_ready, &sense_ready);
+    rc = tick_once(h, a, mask, s, false, true, &keys_ready);
     if (rc) return rc;
     t = 1;
     if (keys_ready) {
       const int pairs = (nsteps - 2) / 2;
-      rc = graph_prepare(h, a, mask, s, &sense_ready);
+      rc = graph_prepare(h, a, mask, s);
       if (rc == PF_OK) {
         for (int p = 0; p < pairs; ++p) {
           PF_CUDA(h, cudaGraphLaunch(h->g_exec, s));
@@ -1336,7 +1258,7 @@ extern "C" int pf_step_ex(pf_handle* h, const pf_agents* a, int nsteps, uint32_t
     }
   }
   for (; t < nsteps; ++t) {
-    rc = tick_once(h, a, mask, s, keys_ready, t + 1 < nsteps, &keys_ready, &sense_ready);
+    rc = tick_once(h, a, mask, s, keys_ready, t + 1 < nsteps, &keys_ready);
     if (rc) return rc;
   }
   return PF_OK;

@@ -331,12 +331,6 @@ class PheroField:
         self._ck(self._L.pf_tile_dense(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def presense_stats(self):
-        """robot-ticks whose sensing was done by the stencil CTA that wrote the cells (pf_presense_stats)"""
-        a = C.c_uint64()
-        self._ck(self._L.pf_presense_stats(self._h, C.byref(a)))
-        return a.value
-
     def profile(self, on: bool):
         self._ck(self._L.pf_profile_enable(self._h, 1 if on else 0))
 
