@@ -580,6 +580,115 @@ def run_single(args):
     field.close()
 
 
+def sharded_side_run(name, steps, warmup, rank, world, local, sort_every=32):
+    """Another BASELINE config on the same ranks, next to the headline of a sharded run: config 4 (two-channel foraging
+    field, clustered population, FSM) on row strips of equal COST, with the per-rank population, strip heights, phase
+    times and foraging counters (BASELINE.json configs[4] names 8 B200: the driver's 8-GPU scaling run carries it).
+    Every rank always reaches the same collectives (a rank that fails says so in them), so a failure here costs the
+    side measurement, never the headline."""
+    import torch
+    import torch.distributed as dist
+
+    from swarm_robotics_pheromones_b200 import sharded
+
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    strip, err = None, None
+    try:
+        cfg, n = make_config(name)
+        x, y, th, st0 = init_agents_torch(cfg, n, "cuda")
+        rows = sharded.agent_rows(cfg, x)
+        per_row = np.bincount(rows, minlength=cfg.H).astype(np.float64)
+        bounds = None
+        if cfg.fsm:  # strips of equal cost: bytes per row = its cells + 260 B (measured DRAM bytes) per robot on it
+            bounds = sharded.weighted_bounds(cfg.W * cfg.C * BYTES_PER_CELL_UPDATE + per_row * 260.0, world, min_rows=256)
+        scfg = sharded.strip_config(cfg, world, rank, device=local, bounds=bounds)
+        mine = np.nonzero((rows >= scfg.row0) & (rows < scfg.row1))[0]
+        mcap = max(4096, int(4 * float(per_row.max())) + 4096)
+        strip = sharded.CudaStrip(scfg, x[mine], y[mine], th[mine], st0[mine], mine.astype(np.uint32),
+                                  int(len(mine) * 1.25) + 4096, mcap)
+        del x, y, th, rows
+    except Exception as e:
+        err = repr(e)
+    if not all_ok(err is None):
+        if strip is not None:
+            strip.field.close()
+        return {"error": err or "another rank could not set up its strip"}
+    ms = 0.0
+    phases = None
+    try:
+        strip.peer_attach_ipc(rank, world)   # collective; every rank is here
+        dist.barrier()
+        strip.peer_prime()
+        strip.peer_wait()
+        drv = sharded.DistDriver(sharded.StripWorker(strip, rank, world))
+        cells = cfg.H * cfg.W * cfg.C
+        sharded.run_ticks(drv, warmup, sort_every, strip.sort_agents)
+        torch.cuda.synchronize()
+    except Exception as e:
+        err = repr(e)
+    dist.barrier()
+    if err is None:
+        try:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sharded.run_ticks(drv, steps, sort_every, strip.sort_agents)   # the timed region pays ceil(K / sort_every) sorts
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            strip.field.peer_status()
+        except Exception as e:
+            err = repr(e)
+    dist.barrier()
+    if err is None:
+        try:  # the same ticks once more with CUDA events at the phase boundaries inside pf_strip_tick (untimed)
+            strip.field.profile(True)
+            sharded.run_ticks(drv, 16, 0, None)
+            torch.cuda.synchronize()
+            phases = strip.field.strip_profile()
+            strip.field.profile(False)
+        except Exception as e:
+            err = repr(e)
+    mine_stats = {"rank": rank, "error": err, "rows": [int(scfg.row0), int(scfg.row1)], "ms": ms, "phases_ms": phases}
+    try:
+        if err is None:
+            c = strip.field.counters()
+            mine_stats.update(agents=int(strip.swarm.alive().sum().item()), food_grabbed=int(c.food_grabbed),
+                              food_delivered=int(c.food_delivered), deposits=int(c.deposits), ticks=int(c.ticks),
+                              migrated_out=int(c.migrated_out), migrate_dropped=int(c.migrate_dropped))
+    except Exception as e:
+        mine_stats["error"] = repr(e)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine_stats)
+    dist.barrier()   # nobody closes its mailboxes while a neighbour may still store into them
+    strip.field.close()
+    errs = [m["error"] for m in everyone if m.get("error")]
+    if errs:
+        return {"error": errs[0]}
+    ms = max(m["ms"] for m in everyone)
+    agents = [m["agents"] for m in everyone]
+    out = {"workload": f"{name}: {cfg.H}x{cfg.W}x{cfg.C}, {n} agents, {cfg.stencil}-point, row strips x{world}",
+           "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "cell_updates_per_s": cells * steps / (ms * 1e-3),
+           "agent_steps_per_s": n * steps / (ms * 1e-3),
+           "strips": "equal cost (cells + robots per row)" if bounds is not None else "equal height",
+           "strip_rows_per_rank": [m["rows"] for m in everyone], "agents_per_rank": agents,
+           "agent_imbalance_max_over_mean": float(max(agents) / max(1.0, float(np.mean(agents)))),
+           "migrated_agents_total": sum(m["migrated_out"] for m in everyone),
+           "migrate_dropped": sum(m["migrate_dropped"] for m in everyone),
+           "phase_ms_per_rank": [m["phases_ms"] for m in everyone],
+           "tick_driver": "pf_strip_tick: one C call per tick, halo rows and leavers through peer mailboxes"}
+    if cfg.fsm:
+        from swarm_robotics_pheromones_b200.metrics import NetEnergy
+        delivered, ticks = sum(m["food_delivered"] for m in everyone), everyone[0]["ticks"]
+        out["foraging"] = {"food_grabbed": sum(m["food_grabbed"] for m in everyone), "food_delivered": delivered,
+                           "deposits": sum(m["deposits"] for m in everyone), "ticks": ticks,
+                           "net_energy": NetEnergy().update(delivered, ticks, n)}
+    return out
+
+
 def run_sharded(args):
     import torch
     import torch.distributed as dist
@@ -589,6 +698,9 @@ def run_sharded(args):
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    same_device = os.environ.get("PF_BENCH_SAME_DEVICE") == "1"   # test mode: every rank on cuda:0, gloo for the set-up
+    if same_device:
+        local = 0
     torch.cuda.set_device(local)
     # stdout carries the one JSON line, so NCCL's log (INFO unless the caller chose a level) goes to a per-rank
     # file and its communicator lines (nranks, transport, NVLS) are copied to STDERR at the end of the run
@@ -598,7 +710,10 @@ def run_sharded(args):
     if "NCCL_DEBUG_FILE" not in os.environ:
         nccl_log = f"/tmp/pf_nccl_{os.getpid()}.log"
         os.environ["NCCL_DEBUG_FILE"] = nccl_log
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if same_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg, n = make_config(args.config, args.grid, args.grid, args.channels, args.agents, args.stencil)
     # every rank draws the same global population and keeps its own strip's agents
     x, y, th, st0 = init_agents_torch(cfg, n, "cuda")
@@ -624,6 +739,8 @@ def run_sharded(args):
         strip.field.set_option(abi.OPT_STRIP_PART_A_TILES, args.part_a_tiles)
     del x, y, th, rows
     strip.field.set_stencil_variant(args.variant, args.rows_per_cta)
+    if same_device:
+        strip.field.set_option(abi.OPT_PEER_TIMEOUT_MS, 30000)  # the ranks time-slice one GPU
     worker = sharded.StripWorker(strip, rank, world)
     legacy = args.legacy_loop or args.nccl_halo
     drv = sharded.DistDriver(worker, overlap=not args.no_overlap, profile=args.phase_profile and legacy, legacy=legacy)
@@ -798,9 +915,19 @@ def run_sharded(args):
         if args.phase_profile:
             line["phase_ms_rank0"] = phases_all[0]
             line["phase_ms_all_ranks"] = phases_all
-        emit(line)
     dist.barrier()
     strip.field.close()
+    # config 4 (BASELINE.json: "... foraging field, 4M agents with nest/food sources, 8 B200") on the same ranks
+    others = None
+    if args.config == "c3" and not args.no_others and (not args.grid or same_device):
+        try:
+            others = {"c4": sharded_side_run("c4", 32, 5, rank, world, local)}
+        except Exception as e:  # collectives out of step would hang, not raise; this is for everything else
+            others = {"c4": {"error": repr(e)}}
+    if rank == 0:
+        line["other_configs"] = others
+        emit(line)
+    dist.barrier()
     dist.destroy_process_group()
     if nccl_log and os.path.exists(nccl_log):  # the communicator lines, for whoever checks the rank count
         keep = ("nranks", "Init COMPLETE", "NVLS", "comm 0x", "NCCL version", "Connected", "P2P")
