@@ -733,8 +733,8 @@ def run_sharded(args):
     strip = sharded.CudaStrip(scfg, x[mine], y[mine], th[mine], st0[mine], mine.astype(np.uint32), cap, mcap)
     if args.force_owner_deposit:
         strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
-    if args.strip_one_launch:
-        strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, 1)
+    if args.strip_one_launch >= 0:
+        strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, args.strip_one_launch)
     if args.part_a_tiles:
         strip.field.set_option(abi.OPT_STRIP_PART_A_TILES, args.part_a_tiles)
     del x, y, th, rows
@@ -970,7 +970,7 @@ def main():
                          "auto = for config 4's clustered population")
     ap.add_argument("--force-owner-deposit", action="store_true",
                     help="sort-free deposit even where the density heuristic prefers the global radix sort")
-    ap.add_argument("--strip-one-launch", action="store_true", help="sharded run: PF_OPT_STRIP_ONE_LAUNCH")
+    ap.add_argument("--strip-one-launch", type=int, default=-1, help="sharded run: PF_OPT_STRIP_ONE_LAUNCH (0, 1, 2); -1 = default")
     ap.add_argument("--part-a-tiles", type=int, default=0, help="sharded run: PF_OPT_STRIP_PART_A_TILES")
     ap.add_argument("--tick-times", action="store_true", help="sharded run: device time of every timed tick (rank 0)")
     ap.add_argument("--legacy-loop", action="store_true",

@@ -461,8 +461,10 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
 #define PF_OPT_NO_TILE_DEPOSIT 6 /* pf_step: never hand the next tick's deposits to the stencil kernel
                                    (default: done where the sort-free deposit is in use and the TMA
                                    stencil runs; falls back on the device when a tile is too crowded) */
-#define PF_OPT_STRIP_ONE_LAUNCH 8 /* pf_strip_tick: step the whole strip in one stencil launch behind the move kernel
-                                    (default off: rows above the handed ones run while the halo is in flight) */
+#define PF_OPT_STRIP_ONE_LAUNCH 8 /* pf_strip_tick: 1 = step the whole strip in one stencil launch behind the move kernel;
+                                    2 = the rows above the handed ones still run while the halo is in flight, the
+                                    handed rows, the band below them and the last row (peer stores included) go in one
+                                    launch; 0 = separate launches */
 #define PF_OPT_STRIP_PART_A_TILES 9 /* strips: tile rows (64 rows each) stepped before the move kernel while the halo is
                                       in flight = the rows that cannot hand their deposits over; 0 = one tile row */
 #define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */

@@ -93,7 +93,7 @@ struct pf_handle {
   int strip_dep0, strip_dep1;  // pf_strip_tick: rows handed over this tick (phase A decides, B and C use)
   bool strip_active;
   bool strip_one_launch;      // set while pf_strip_tick drives the strip in one-launch mode (see strip_tile_range)
-  bool strip_one_launch_opt;  // PF_OPT_STRIP_ONE_LAUNCH
+  int strip_one_launch_opt;   // PF_OPT_STRIP_ONE_LAUNCH: 0 off, 1 the whole strip, 2 the handed rows and everything below them
   int strip_part_a_tiles;     // PF_OPT_STRIP_PART_A_TILES (0 = an eighth of the strip)
   // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
   cudaEvent_t* strip_ev;
@@ -588,8 +588,9 @@ static PeerRows peer_rows(const pf_handle* h, int k) {
 // with_deposits: the next tick's deposits ride along (the lists of the tile rows tile_ty0..ty1 are ready).
 // whole_strip (with_deposits only): the launch covers every tile row of the strip, edge rows with their peer
 // stores included — the tiles outside tile_ty0..ty1 have empty lists.
+// to_end (with_deposits only): from the first handed tile row to the strip's last row, its peer stores included.
 static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, bool with_deposits = false,
-                          bool whole_strip = false) {
+                          bool whole_strip = false, bool to_end = false) {
   if (r_begin >= r_end) return PF_OK;
   const PFDev& d = h->dev;
   StencilArgs a;
@@ -609,6 +610,7 @@ static int launch_stencil(pf_handle* h, int r_begin, int r_end, cudaStream_t s, 
     a.dep_dense = h->tile_dense; a.dep_side = h->tile_side;
     const int ny = (d.rows + kTileRows - 1) / kTileRows;
     int rc = whole_strip ? tma_stencil_launch_dep(&h->tma, d, a, 0, ny, true, s)
+             : to_end    ? tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, ny, true, s)
                          : tma_stencil_launch_dep(&h->tma, d, a, h->tile_ty0, h->tile_ty1, false, s);
     if (rc != PF_OK) return set_err(h, rc, "TMA stencil launch failed: %s", h->tma.err);
     h->launches++;
@@ -707,7 +709,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_NO_OWNER_DEPOSIT) { h->no_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_FORCE_OWNER_DEPOSIT) { h->force_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_PART_A_TILES) { h->strip_part_a_tiles = value > 0 ? value : 0; return PF_OK; }
-  if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value != 0; return PF_OK; }
+  if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value < 0 ? 0 : (value > 2 ? 2 : value); return PF_OK; }
   if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
@@ -1618,7 +1620,7 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       h->strip_mark = 0;
     }
     STRIP_MARK();  // 0: start
-    h->strip_one_launch = h->strip_one_launch_opt;
+    h->strip_one_launch = h->strip_one_launch_opt == 1;
     h->strip_dep0 = h->strip_dep1 = 0;
     if ((flags & PF_STEP_HANDOVER) && dep && move && (flags & PF_STEP_SENSE) && a->n > 0) {
       int ty0, ty1;
@@ -1668,7 +1670,15 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       h->tile_handed = true;
     } else {
       bool last_done = false;
-      if (handing) {
+      if (handing && h->strip_one_launch_opt == 2 && h->tile_pending) {
+        // the handed rows, the band below them and the last row (peer stores included) in one launch: the tiles of
+        // the band simply have no passengers
+        rc = launch_stencil(h, h->strip_dep0, rows, s, true, false, true);
+        if (rc) return rc;
+        h->tile_pending = false;
+        h->tile_handed = true;
+        last_done = true;
+      } else if (handing) {
         rc = pf_step_field_rows(h, h->strip_dep0, h->strip_dep1, stream);  // exactly these rows: the deposits ride along
         if (rc) return rc;
         last_done = true;

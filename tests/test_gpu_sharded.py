@@ -52,7 +52,7 @@ def test_strips_equal_unsharded_bitexact(world, variant, peer):
         w.b.field.close()
 
 
-@pytest.mark.parametrize("peer", [False, True, "one-launch", "part-a-1"])
+@pytest.mark.parametrize("peer", [False, True, "one-launch", "fold-below", "part-a-1"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
     # strips tall enough to have interior tile rows (64 rows x 1024 columns): the move kernel hands the
@@ -72,6 +72,8 @@ def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
         strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)  # 4-7 k robots per strip: below the default threshold
         if peer == "one-launch":  # the whole strip in one stencil launch behind the move kernel (PF_OPT_STRIP_ONE_LAUNCH)
             strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, 1)
+        if peer == "fold-below":  # the handed rows, the band below them and the last row in one launch (value 2)
+            strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, 2)
         if peer == "part-a-1":    # only the first tile row runs before the move kernel; every other row hands over
             strip.field.set_option(abi.OPT_STRIP_PART_A_TILES, 1)
         workers.append(sharded.StripWorker(strip, r, world))

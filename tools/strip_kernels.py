@@ -22,6 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--world", type=int, default=8)
 ap.add_argument("--ticks", type=int, default=6)
 ap.add_argument("--config", default="c3")
+ap.add_argument("--one-launch", type=int, default=-1, help="PF_OPT_STRIP_ONE_LAUNCH (0, 1, 2); -1 = the library default")
 ap.add_argument("--strips", type=int, default=0, help="materialise only the first K strips (0 = all): saves memory")
 args = ap.parse_args()
 
@@ -35,6 +36,8 @@ for r in range(G):
     mine = np.nonzero((rows >= scfg.row0) & (rows < scfg.row1))[0]
     strip = sharded.CudaStrip(scfg, x[mine], y[mine], th[mine], st[mine], mine.astype(np.uint32),
                               int(len(mine) * 1.25) + 4096, 8192)
+    if args.one_launch >= 0:
+        strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, args.one_launch)
     workers.append(sharded.StripWorker(strip, r, G))
 drv = sharded.LocalDriver(workers)
 drv.attach_peers()
