@@ -819,32 +819,23 @@ def run_sharded(args):
     local_cells = strip.rows * cfg.W * cfg.C
     ach = local_cells * BYTES_PER_CELL_UPDATE / (st_ms * 1e-3) / 1e9
 
-    # e2e: per-rank host poses in, wheel speeds out, no motion on the device
+    # e2e: per-rank host poses in, wheel speeds out, no motion on the device (sharded.StripHostTick: the strip's
+    # counterpart of ReferenceCompat.tick_host)
     sw = strip.swarm
     nl = sw.n
+    host = sharded.StripHostTick(strip, worker)
     h_pose = torch.empty((3, nl), dtype=torch.float32).pin_memory()
-    d_pose = torch.empty((3, nl), dtype=torch.float32, device="cuda")
-    h_out = torch.empty((2, nl), dtype=torch.float32).pin_memory()
     h_pose[0].copy_(sw.x.cpu()); h_pose[1].copy_(sw.y.cpu()); h_pose[2].copy_(sw.theta.cpu())
     h_pose_b = torch.empty_like(h_pose).pin_memory()
     h_pose_b.copy_(h_pose)
     h_pose_b[1].add_(3e-3)  # along y: no agent changes strip, every agent has moved
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    d_dec = torch.empty(nl, dtype=torch.uint8, device="cuda")
-    h_dec = torch.empty(nl, dtype=torch.uint8).pin_memory()
     e2e_k = [0]
 
     def e2e_tick():
         src = h_pose_b if e2e_k[0] % 2 == 0 else h_pose
         e2e_k[0] += 1
-        d_pose.copy_(src, non_blocking=True)
-        strip.field.observe(sw, d_pose[0], d_pose[1], d_pose[2])
-        drv.tick(True, move=False)
-        h_out[0].copy_(sw.wl, non_blocking=True)
-        h_out[1].copy_(sw.wr, non_blocking=True)
-        d_dec.copy_((sw.meta & abi.META_DEC_MASK) >> abi.META_DEC_SHIFT)
-        h_dec.copy_(d_dec, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        host.tick(src)   # returns when this rank's speeds and decisions are on the host
 
     e2e_tick()
     dist.barrier()
@@ -856,8 +847,7 @@ def run_sharded(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
-    bytes_io = torch.tensor([h_pose.numel() * 4, h_out.numel() * 4 + h_dec.numel()], device="cuda",
-                            dtype=torch.float64)
+    bytes_io = torch.tensor([host.h2d_bytes, host.d2h_bytes], device="cuda", dtype=torch.float64)
     dist.all_reduce(bytes_io)
     counts = torch.tensor([float(sw.alive().sum().item())], device="cuda", dtype=torch.float64)
     allc = [torch.zeros_like(counts) for _ in range(world)]
@@ -887,7 +877,8 @@ def run_sharded(args):
                     "agent_steps_per_s": n * e2e_steps / e2e_s, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "steps": e2e_steps, "h2d_bytes_per_step": int(bytes_io[0].item()),
                     "d2h_bytes_per_step": int(bytes_io[1].item()),
-                    "call": "per rank: pinned poses -> pf_agents_observe -> sharded tick -> speeds to host"},
+                    "call": "per rank: sharded.StripHostTick.tick(pinned poses [3][slots]) -> (wl, wr, decision) on host; "
+                            "pf_strip_tick phases A+B, D2H beside phase C"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "evaporate+diffuse stencil (rank 0 strip, timed alone)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

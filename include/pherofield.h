@@ -467,6 +467,9 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
                                     launch; 0 = separate launches */
 #define PF_OPT_STRIP_PART_A_TILES 9 /* strips: tile rows (64 rows each) stepped before the move kernel while the halo is
                                       in flight = the rows that cannot hand their deposits over; 0 = one tile row */
+#define PF_OPT_STRIP_MIG_INLINE 11 /* pf_strip_tick: keep the migration kernels (pack, signal, wait, unpack) on the caller's
+                                     stream, in line with the stencil launches (default 0: they run beside the stencil
+                                     on the handle's side stream and the caller's stream joins them at the end of the tick) */
 #define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */

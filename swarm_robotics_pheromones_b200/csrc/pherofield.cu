@@ -95,6 +95,7 @@ struct pf_handle {
   bool strip_one_launch;      // set while pf_strip_tick drives the strip in one-launch mode (see strip_tile_range)
   int strip_one_launch_opt;   // PF_OPT_STRIP_ONE_LAUNCH: 0 off, 1 the whole strip, 2 the handed rows and everything below them
   int strip_part_a_tiles;     // PF_OPT_STRIP_PART_A_TILES (0 = an eighth of the strip)
+  int strip_mig_inline;       // PF_OPT_STRIP_MIG_INLINE: migration on the caller's stream instead of beside the stencil
   // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
   cudaEvent_t* strip_ev;
   int strip_used, strip_mark;
@@ -710,6 +711,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_FORCE_OWNER_DEPOSIT) { h->force_owner_deposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_PART_A_TILES) { h->strip_part_a_tiles = value > 0 ? value : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value < 0 ? 0 : (value > 2 ? 2 : value); return PF_OK; }
+  if (option == PF_OPT_STRIP_MIG_INLINE) { h->strip_mig_inline = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
@@ -1658,7 +1660,16 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       if (handing && !h->tile_pending) return set_err(h, PF_ESTATE, "pf_strip_tick: hand-over range changed inside a tick");
     }
     STRIP_MARK();  // 4: sense/decide/move (+ bins + grouping)
-    if (move) { rc = strip_pack(h, a, s); if (rc) return rc; }
+    // Migration (pack -> signal -> wait -> unpack: six small latency-bound kernels that only touch the agent arrays
+    // and the mailboxes) runs on the handle's side stream, beside the stencil launches of phase C, which only touch
+    // the field and the tile lists; the caller's stream joins it at the end of the tick, so the next tick's deposit
+    // and halo signal still come behind this tick's unpack (what the one-mailbox protocol above relies on).
+    const bool mig_side = move && !h->strip_mig_inline;
+    if (mig_side) {
+      PF_CUDA(h, cudaEventRecord(h->ev_fork, s));
+      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    }
+    if (move) { rc = strip_pack(h, a, mig_side ? h->side : s); if (rc) return rc; }
     STRIP_MARK();  // 5: pack + migration signal
   }
   if (phases & PF_TICK_C) {  // the remaining rows (handed deposits ride along), swap, arrivals in
@@ -1694,13 +1705,19 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     rc = pf_swap(h);
     if (rc) return rc;
     STRIP_MARK();  // 6: stencil
+    const bool mig_side = move && !h->strip_mig_inline;
+    cudaStream_t ms = mig_side ? h->side : s;
     if (move && (h->peer_up.set || h->peer_dn.set)) {
-      k_peer_wait<<<1, 1, 0, s>>>(h->peer_up.set ? h->peer_flags + 2 : nullptr, h->peer_dn.set ? h->peer_flags + 3 : nullptr,
-                                  h->mig_epoch, h->peer_timeout_ns, h->counters);
+      k_peer_wait<<<1, 1, 0, ms>>>(h->peer_up.set ? h->peer_flags + 2 : nullptr, h->peer_dn.set ? h->peer_flags + 3 : nullptr,
+                                   h->mig_epoch, h->peer_timeout_ns, h->counters);
       PF_LAUNCH_CHECK(h);
     }
     STRIP_MARK();  // 7: migration wait
-    if (move) { rc = strip_unpack(h, a, s); if (rc) return rc; }
+    if (move) { rc = strip_unpack(h, a, ms); if (rc) return rc; }
+    if (mig_side) {  // join: everything the caller enqueues next is ordered behind the unpack
+      PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+      PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    }
     k_tick_counter<<<1, 1, 0, s>>>(h->counters);
     PF_LAUNCH_CHECK(h);
     STRIP_MARK();  // 8: unpack

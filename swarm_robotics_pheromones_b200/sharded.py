@@ -509,6 +509,52 @@ class DistDriver:
             w.ticks += 1
 
 
+class StripHostTick:
+    """The host-facing tick of ONE strip (one process per GPU) — what `ReferenceCompat.tick_host` is on a single GPU:
+    this rank's robots' poses come from pinned host memory ([3][slots]: x, y, theta in slot order), their wheel speeds
+    and decisions go back to pinned host memory, the caller (Webots in the reference) owns the motion, so nothing
+    moves or migrates on the device. The tick itself is `pf_strip_tick` in two calls: deposit, halo signal, first rows,
+    halo wait, sense/decide (phases A and B), then the speeds start their way to the host on a side stream while the
+    rest of the strip is stepped (phase C) — the supervisor needs the speeds, not the field."""
+
+    def __init__(self, strip: "CudaStrip", worker: "StripWorker"):
+        self.strip, self.w = strip, worker
+        sw = strip.swarm
+        n, dev = sw.n, sw.x.device
+        self.d_pose = torch.empty((3, n), dtype=torch.float32, device=dev)
+        self.d_dec = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.h_out = torch.empty((2, n), dtype=torch.float32).pin_memory()
+        self.h_dec = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self.side = torch.cuda.Stream(dev)
+        self.ev_b, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
+        self.h2d_bytes = self.d_pose.numel() * 4
+        self.d2h_bytes = self.h_out.numel() * 4 + self.h_dec.numel()
+
+    def tick(self, pose_host: torch.Tensor, sense_enabled: bool = True):
+        strip, sw = self.strip, self.strip.swarm
+        main = torch.cuda.current_stream(sw.x.device)
+        self.d_pose.copy_(pose_host, non_blocking=True)
+        if sense_enabled:
+            strip.field.observe(sw, self.d_pose[0], self.d_pose[1], self.d_pose[2])
+        else:  # before the start delay the reference stores no poses (sup:279-289 runs inside deposit_pheromone only)
+            sw.x.copy_(self.d_pose[0]); sw.y.copy_(self.d_pose[1]); sw.theta.copy_(self.d_pose[2])
+        flags = strip_flags(sense_enabled, False, False)
+        strip.strip_tick(flags, abi.TICK_A | abi.TICK_B)
+        self.ev_b.record(main)
+        with torch.cuda.stream(self.side):      # the speeds leave beside the rest of the strip's stencil
+            self.side.wait_event(self.ev_b)
+            self.h_out[0].copy_(sw.wl, non_blocking=True)
+            self.h_out[1].copy_(sw.wr, non_blocking=True)
+            self.d_dec.copy_((sw.meta & abi.META_DEC_MASK) >> abi.META_DEC_SHIFT)
+            self.h_dec.copy_(self.d_dec, non_blocking=True)
+            self.ev_out.record(self.side)
+        strip.strip_tick(flags, abi.TICK_C)
+        self.w.ticks += 1
+        main.wait_event(self.ev_out)            # the next tick's kernels rewrite wl / wr / meta
+        self.ev_out.synchronize()
+        return self.h_out[0], self.h_out[1], self.h_dec
+
+
 def strip_flags(sense_enabled: bool, move: bool, hand_over: bool) -> int:
     """pf_strip_tick flags of a tick (deposit and sensing start together, sup:581)"""
     f = abi.STEP_FIELD

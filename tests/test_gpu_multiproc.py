@@ -25,9 +25,10 @@ def _torchrun(nproc, port, *tool_args, timeout=420):
 def test_two_processes_on_one_gpu_mailbox_protocol_bitexact():
     # both ranks on cuda:0 (gloo carries the set-up; NCCL refuses two ranks on one device): the cross-process
     # protocol itself — IPC mappings, remote flag words, bounded waits — on a box with a single GPU
-    rc, out = _torchrun(2, 29671, "--peer", "--same-device", "--ticks", "40", "--grid", "1024", "--agents", "60000")
+    rc, out = _torchrun(2, 29671, "--peer", "--same-device", "--ticks", "40", "--grid", "1024", "--agents", "60000",
+                       "--host-ticks", "3")   # + the host-facing tick of a strip (sharded.StripHostTick)
     assert rc == 0 and "-> PASS" in out, out[-3000:]
-    assert "pf_strip_tick + mailbox migration" in out
+    assert "pf_strip_tick + mailbox migration" in out and "3 host-facing ticks" in out
 
 
 @pytest.mark.timeout(900)
@@ -36,5 +37,6 @@ def test_nccl_ranks_on_separate_gpus_bitexact():
     if n < 2:
         pytest.skip("needs at least 2 GPUs (run by tools/dist_parity.py under gpurun --gpus N; outputs in profiles/)")
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
-    rc, out = _torchrun(world, 29673, "--peer", "--ticks", "100", "--grid", "4096", "--agents", "1200000")
+    rc, out = _torchrun(world, 29673, "--peer", "--ticks", "100", "--grid", "4096", "--agents", "1200000",
+                        "--host-ticks", "3")
     assert rc == 0 and "-> PASS" in out, out[-3000:]

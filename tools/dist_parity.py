@@ -31,6 +31,9 @@ ap.add_argument("--sort-every", type=int, default=16)
 ap.add_argument("--no-hand-over", action="store_true")
 ap.add_argument("--peer", action="store_true", help="peer-store halo (CUDA IPC + NVLink P2P) instead of NCCL")
 ap.add_argument("--legacy", action="store_true", help="phase-by-phase host loop with NCCL migration (round 1)")
+ap.add_argument("--host-ticks", type=int, default=0,
+                help="after the ticks: this many host-facing ticks (sharded.StripHostTick: pinned poses in, speeds out, "
+                     "no motion on the device) against observe + pf_step_ex without PF_STEP_MOVE on the unsharded field")
 ap.add_argument("--same-device", action="store_true", help="all ranks on cuda:0, gloo for the set-up")
 args = ap.parse_args()
 
@@ -83,6 +86,31 @@ for t in range(args.ticks):
         strip.field.peer_status()  # stop early (raises) instead of piling up timeouts if the ranks cannot overlap
 torch.cuda.synchronize()
 
+
+def host_pose(xv, yv, thv, gid, k):
+    """the 'physics' of host tick k: every robot shifted along y by a gid-dependent step (nobody changes strip)"""
+    step = ((gid.to(torch.int64) + k) % 5 - 2).to(torch.float32) * 1.5e-3
+    ymax = W * 0.01 - 0.02
+    return xv, torch.clamp(yv + step, 0.02, ymax), thv
+
+
+host_ok = True
+if args.host_ticks:
+    host = sharded.StripHostTick(strip, drv.w)
+    sw_ = strip.swarm
+    pose = torch.empty((3, sw_.n), dtype=torch.float32).pin_memory()
+    for k in range(args.host_ticks):
+        nx, ny, nth = host_pose(sw_.x, sw_.y, sw_.theta, sw_.gid, k)
+        pose[0].copy_(nx); pose[1].copy_(ny); pose[2].copy_(nth)
+        torch.cuda.synchronize()
+        wl, wr, dec = host.tick(pose)
+        # what arrived on the host is what the device holds
+        host_ok = host_ok and bool((wl.view(torch.int32) == sw_.wl.cpu().view(torch.int32)).all())
+        host_ok = host_ok and bool((wr.view(torch.int32) == sw_.wr.cpu().view(torch.int32)).all())
+        want_dec = ((sw_.meta & abi.META_DEC_MASK) >> abi.META_DEC_SHIFT).to(torch.uint8).cpu()
+        host_ok = host_ok and bool((dec == want_dec).all())
+    torch.cuda.synchronize()
+
 strip.field.peer_status()  # raises if a bounded peer wait gave up
 
 # gather strips on rank 0
@@ -101,6 +129,10 @@ if rank == 0:
     g = PheroField(cfg)
     s1 = Swarm(x, y, th, st)
     g.step(s1, args.ticks)
+    for k in range(args.host_ticks):
+        nx, ny, nth = host_pose(s1.x, s1.y, s1.theta, s1.gid, k)
+        g.observe(s1, nx.clone(), ny.clone(), nth.clone())
+        g.step(s1, 1, abi.STEP_DEPOSIT | abi.STEP_SENSE | abi.STEP_FIELD)
     torch.cuda.synchronize()
     want_f = g.snapshot()
     w = s1.to_numpy()
@@ -112,10 +144,19 @@ if rank == 0:
         for k, f in enumerate(("x", "y", "theta", "wl", "wr", "meta")))
     mig = strip.field.counters()
     ok = same_field and same_agents
+    if args.host_ticks:
+        print(f"dist_parity: {args.host_ticks} host-facing ticks (StripHostTick) included in the comparison", flush=True)
     att, fb = strip.field.tile_stats()
     print(f"dist_parity world={world} hand-over ticks on rank 0: {att} (fell back {fb}); peer_halo={args.peer} path={'legacy host loop + NCCL migration' if (args.legacy or not args.peer) else 'pf_strip_tick + mailbox migration'} ticks={args.ticks} grid={H} agents={n}: field_bitexact={same_field} "
           f"agents_bitexact={same_agents} (rank0 migrated_out={mig.migrated_out}, dropped={mig.migrate_dropped}) "
           f"-> {'PASS' if ok else 'FAIL'}", flush=True)
+if args.host_ticks:  # every rank's host buffers held what its device arrays hold
+    flag = torch.tensor([1 if host_ok else 0], dtype=torch.int32, device="cuda" if not args.same_device else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not bool(flag.item()):
+        ok = False
+        if rank == 0:
+            print("dist_parity: host buffers differ from the device arrays -> FAIL", flush=True)
 dist.barrier()
 strip.field.close()
 dist.destroy_process_group()

@@ -21,8 +21,10 @@ from swarm_robotics_pheromones_b200 import abi, sharded  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--world", type=int, default=8)
 ap.add_argument("--ticks", type=int, default=6)
+ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--config", default="c3")
 ap.add_argument("--one-launch", type=int, default=-1, help="PF_OPT_STRIP_ONE_LAUNCH (0, 1, 2); -1 = the library default")
+ap.add_argument("--mig-inline", type=int, default=-1, help="PF_OPT_STRIP_MIG_INLINE; -1 = the library default")
 ap.add_argument("--strips", type=int, default=0, help="materialise only the first K strips (0 = all): saves memory")
 args = ap.parse_args()
 
@@ -38,16 +40,26 @@ for r in range(G):
                               int(len(mine) * 1.25) + 4096, 8192)
     if args.one_launch >= 0:
         strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, args.one_launch)
+    if args.mig_inline >= 0:
+        strip.field.set_option(abi.OPT_STRIP_MIG_INLINE, args.mig_inline)
     workers.append(sharded.StripWorker(strip, r, G))
 drv = sharded.LocalDriver(workers)
 drv.attach_peers()
 for w in workers:
     w.b.sort_agents()
+sharded.run_ticks(drv, 8)   # warm-up: lazy allocations, clocks
 torch.cuda.synchronize()
-t0 = time.perf_counter()
-sharded.run_ticks(drv, args.ticks)
-torch.cuda.synchronize()
-print(f"{G} strips, {args.ticks} ticks: {(time.perf_counter() - t0) / args.ticks * 1e3:.3f} ms per tick for ALL strips on one GPU")
+reps = []
+for _ in range(args.reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sharded.run_ticks(drv, args.ticks)
+    e1.record()
+    torch.cuda.synchronize()
+    reps.append(e0.elapsed_time(e1) / args.ticks)
+print(f"{G} strips, {args.reps} x {args.ticks} ticks (the last one of each run without hand-over): "
+      f"{' / '.join(f'{r:.3f}' for r in reps)} ms per tick for ALL strips on one GPU (CUDA events), "
+      f"best {min(reps) / G:.4f} ms per strip tick")
 for w in workers:
     w.b.field.peer_status()
     w.b.field.close()
