@@ -470,6 +470,10 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
 #define PF_OPT_STRIP_MIG_INLINE 11 /* pf_strip_tick: keep the migration kernels (pack, signal, wait, unpack) on the caller's
                                      stream, in line with the stencil launches (default 0: they run beside the stencil
                                      on the handle's side stream and the caller's stream joins them at the end of the tick) */
+#define PF_OPT_STRIP_NO_PREDEPOSIT 12 /* pf_strip_tick: keep the whole deposit at the start of the tick (default 0: on a hand-over
+                                        tick the NEXT tick's deposit of the robots that were not handed over — edge bands and
+                                        arrivals — runs at the end of the tick on the side stream, behind the unpack and beside
+                                        the stencil launch that carries the handed robots' deposits) */
 #define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */

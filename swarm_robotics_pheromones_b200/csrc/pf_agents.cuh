@@ -16,13 +16,21 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
                       const float* __restrict__ y, uint32_t* __restrict__ meta,
                       uint32_t* __restrict__ keys, float* __restrict__ vals, uint32_t sentinel,
                       unsigned long long* __restrict__ counters, uint32_t* __restrict__ cmin,
-                      uint32_t* __restrict__ cmax, TileBins handed, uint32_t* __restrict__ handed_flag) {
+                      uint32_t* __restrict__ cmax, TileBins handed, uint32_t* __restrict__ handed_flag, int mode,
+                      int late_may_skip) {
   // handed.bcnt != null: the last move kernel handed the deposits of the tile rows [ty_lo, ty_hi)
   // to the stencil (counter already bumped). *handed_flag == 0: the stencil applied them, nothing
   // left to do for those agents; != 0: it could not (a crowded tile) and they are deposited here
   // after all, with the amount their bumped counter says.
+  // mode (pf_strip_tick's deposit in two parts, see there): 0 = everybody in one pass, as described;
+  // 1 = EARLY, at the end of the tick that handed over, beside its stencil launch: only the robots that were NOT
+  // handed over (their cells, the edge bands, are stepped already); the handed ones are left alone, mark and all;
+  // 2 = LATE, at the start of the next tick: only the handed robots — nothing at all if the stencil applied their
+  // deposits and the coming move kernel clears the marks (late_may_skip), else marks cleared and, on a raised flag,
+  // deposited after all. The two parts never share a cell (pf_tile_rows), so two passes round like one.
   const bool handed_done = handed.bcnt && *handed_flag == 0u;
-  if (handed.bcnt && !handed_done && blockIdx.x == 0 && threadIdx.x == 0) handed_flag[1] += 1u;  // pf_tile_stats
+  if (mode == 2 && handed_done && late_may_skip) return;
+  if (mode == 0 && handed.bcnt && !handed_done && blockIdx.x == 0 && threadIdx.x == 0) handed_flag[1] += 1u;  // pf_tile_stats
   // grid-stride over a fixed grid (a multiple of the SM count): the deposit counter costs one
   // global atomic per CTA instead of one per warp (same-address atomics serialise in L2)
   __shared__ unsigned int s_dep;
@@ -39,11 +47,12 @@ k_deposit_keys_agents(PFDev p, long long n, const float* __restrict__ x,
     // the move kernel marked the robots whose deposit it handed to the stencil (PF_META_HANDED): the
     // mark, not the position, says who they are — poses may have been replaced since (pf_agents_observe)
     const bool was_handed = (mt & PF_META_HANDED) != 0u;
-    if (was_handed) {
+    const bool skip = (mode == 1 && was_handed) || (mode == 2 && !was_handed);  // the other pass's robot
+    if (was_handed && !skip) {
       mt &= ~PF_META_HANDED;
       meta[i] = mt;
     }
-    if ((st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && ((mt & PF_META_MOVED) || was_handed)) {
+    if (!skip && (st == PF_STATE_SEARCHING || st == PF_STATE_HOMING) && ((mt & PF_META_MOVED) || was_handed)) {
       int r, q;
       bool inside = pf_cell(p, x[i], y[i], r, q);
       int ch = p.dep_ch[st];
@@ -251,6 +260,8 @@ k_agents_step(PFDev p, const float* __restrict__ f, uint32_t flags, long long n,
        i += (long long)gridDim.x * blockDim.x) {
     uint32_t mt = ameta[i];
     uint32_t st = mt & PF_META_STATE_MASK;
+    // a mark left by the LATE deposit pass that had nothing to do (pf_strip_tick): its tick's deposit is over
+    mt &= ~PF_META_HANDED;
     if (st == PF_STATE_EMPTY) {
       if (dec_out) dec_out[i] = PF_DEC_NONE;
       if (next_keys) { next_keys[i] = sentinel; next_vals[i] = 0.0f; }

@@ -96,6 +96,9 @@ struct pf_handle {
   int strip_one_launch_opt;   // PF_OPT_STRIP_ONE_LAUNCH: 0 off, 1 the whole strip, 2 the handed rows and everything below them
   int strip_part_a_tiles;     // PF_OPT_STRIP_PART_A_TILES (0 = an eighth of the strip)
   int strip_mig_inline;       // PF_OPT_STRIP_MIG_INLINE: migration on the caller's stream instead of beside the stencil
+  int strip_no_predeposit;    // PF_OPT_STRIP_NO_PREDEPOSIT
+  bool strip_predep;          // the EARLY part of the next tick's deposit is enqueued (behind this tick's unpack)
+  cudaEvent_t ev_edges;       // the strip's edge rows of this tick are stepped
   // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
   cudaEvent_t* strip_ev;
   int strip_used, strip_mark;
@@ -363,6 +366,7 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
   }
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_edges, cudaEventDisableTiming));
   {
     int occ = 0;
     CREATE_CUDA(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -411,6 +415,7 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_edges) cudaEventDestroy(h->ev_edges);
   if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
   if (h->g_graph) cudaGraphDestroy(h->g_graph);
   if (h->prof_ev) {
@@ -712,6 +717,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_STRIP_PART_A_TILES) { h->strip_part_a_tiles = value > 0 ? value : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value < 0 ? 0 : (value > 2 ? 2 : value); return PF_OK; }
   if (option == PF_OPT_STRIP_MIG_INLINE) { h->strip_mig_inline = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_STRIP_NO_PREDEPOSIT) { h->strip_no_predeposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
   return set_err(h, PF_EINVAL, "unknown option %d", option);
@@ -916,17 +922,16 @@ static int check_agents(pf_handle* h, const pf_agents* a) {
   return PF_OK;
 }
 
-extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream) {
-  int rc = check_agents(h, a);
-  if (rc) return rc;
-  if (a->n == 0) return PF_OK;
-  rc = pf_reserve_agents(h, a->n);
-  if (rc) return rc;
-  PF_CUDA(h, cudaSetDevice(h->cfg.device));
-  cudaStream_t s = (cudaStream_t)stream;
+// mode 0: the whole deposit. mode 1 (EARLY) / the call after it (LATE): pf_strip_tick's deposit in two parts — the
+// robots that were not handed over at the end of the hand-over tick (on the side stream, beside the stencil launch
+// that carries the handed ones), the handed ones at the start of the next tick, which is nothing but three
+// launches that return at once unless the stencil could not apply them.
+static int agents_deposit(pf_handle* h, const pf_agents* a, cudaStream_t s, int mode, int late_may_skip) {
   uint32_t* keys_in = (uint32_t*)h->scratch;
   float* vals_in = (float*)(keys_in + 2 * h->cap);
   const bool own = owner_ready(h, a);
+  if (mode != 0 && (!own || !h->tile_handed))
+    return set_err(h, PF_ESTATE, "two-part deposit without a hand-over tick behind it");
   TileBins handed;
   memset(&handed, 0, sizeof(handed));
   h->own_handed_lo = h->own_handed_hi = 0;
@@ -936,17 +941,35 @@ extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream)
     handed.ny = (h->dev.rows + kTileRows - 1) / kTileRows;
     handed.ty_lo = h->tile_ty0;
     handed.ty_hi = h->tile_ty1;
-    h->tile_handed = false;
-    const long long r1 = (long long)h->tile_ty1 * kTileRows < h->dev.rows ? (long long)h->tile_ty1 * kTileRows : h->dev.rows;
-    h->own_handed_lo = (uint32_t)((long long)h->tile_ty0 * kTileRows * h->dev.W);
-    h->own_handed_hi = (uint32_t)(r1 * h->dev.W);
+    if (mode != 1) h->tile_handed = false;   // EARLY: the tick is still "one ahead" until the LATE part has run
+    if (mode != 2) {  // (LATE deposits exactly the handed rows, if anything)
+      const long long r1 = (long long)h->tile_ty1 * kTileRows < h->dev.rows ? (long long)h->tile_ty1 * kTileRows : h->dev.rows;
+      h->own_handed_lo = (uint32_t)((long long)h->tile_ty0 * kTileRows * h->dev.W);
+      h->own_handed_hi = (uint32_t)(r1 * h->dev.W);
+    }
   }
   k_deposit_keys_agents<<<wave_grid(a->n, h->wave_keys), 256, 0, s>>>(h->dev, a->n, a->x, a->y, a->meta, keys_in,
                                                              vals_in, h->sentinel, h->counters,
                                                              own ? h->own_cmin : nullptr,
-                                                             own ? h->own_cmax : nullptr, handed, h->tile_flag);
+                                                             own ? h->own_cmax : nullptr, handed, h->tile_flag, mode,
+                                                             late_may_skip);
   PF_LAUNCH_CHECK(h);
+  if (mode == 2) return owner_sum(h, a->n, s, h->tile_flag);   // only if the stencil could not apply them
   return own ? owner_sum(h, a->n, s) : sort_and_sum(h, a->n, s);
+}
+
+extern "C" int pf_agents_deposit(pf_handle* h, const pf_agents* a, void* stream) {
+  int rc = check_agents(h, a);
+  if (rc) return rc;
+  if (a->n == 0) return PF_OK;
+  rc = pf_reserve_agents(h, a->n);
+  if (rc) return rc;
+  PF_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (h->strip_predep) {  // the other robots were deposited at the end of the last pf_strip_tick
+    h->strip_predep = false;
+    return agents_deposit(h, a, (cudaStream_t)stream, 2, 0);
+  }
+  return agents_deposit(h, a, (cudaStream_t)stream, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1631,7 +1654,13 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
         h->strip_dep1 = ty1 * kTileRows < rows ? ty1 * kTileRows : rows;
       }
     }
-    if (dep && a->n > 0) { rc = pf_agents_deposit(h, a, stream); if (rc) return rc; }
+    if (h->strip_predep) {  // the robots that were not handed over deposited at the end of the last tick (phase C)
+      if (!dep || a->n == 0)
+        return set_err(h, PF_ESTATE, "pf_strip_tick: the tick after a hand-over tick must deposit (PF_STEP_DEPOSIT)");
+      h->strip_predep = false;
+      rc = agents_deposit(h, a, s, 2, (flags & (PF_STEP_SENSE | PF_STEP_MOVE)) ? 1 : 0);
+      if (rc) return rc;
+    } else if (dep && a->n > 0) { rc = pf_agents_deposit(h, a, stream); if (rc) return rc; }
     STRIP_MARK();  // 1: deposit
     rc = pf_peer_signal(h, stream);
     if (rc) return rc;
@@ -1674,6 +1703,8 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
   }
   if (phases & PF_TICK_C) {  // the remaining rows (handed deposits ride along), swap, arrivals in
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase C without phase A");
+    const bool mig_side_c = move && !h->strip_mig_inline;
+    bool predep_c = false;
     if (one_launch) {  // every row of the strip, edge rows and their peer stores included, in one launch
       rc = launch_stencil(h, 0, rows, s, true, true);
       if (rc) return rc;
@@ -1681,7 +1712,21 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       h->tile_handed = true;
     } else {
       bool last_done = false;
-      if (handing && h->strip_one_launch_opt == 2 && h->tile_pending) {
+      // Deposit in two parts: a hand-over tick promises that a depositing tick follows, and that tick's deposit of
+      // the robots NOT handed over (edge bands, arrivals) only needs this tick's edge rows and its unpack. So the edge
+      // rows are stepped first, and behind the unpack the side stream runs that deposit beside the big launch that
+      // carries the handed robots' deposits; the next tick starts with its halo signal almost at once.
+      const bool predep = handing && h->tile_pending && mig_side_c && dep && a->n > 0 && !h->strip_no_predeposit &&
+                          h->strip_one_launch_opt != 2 && (h->peer_up.set || h->peer_dn.set);
+      if (predep) {
+        if (h->strip_dep1 < rows) { rc = launch_stencil(h, h->strip_dep1, rows, s); if (rc) return rc; }
+        rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
+        if (rc) return rc;
+        PF_CUDA(h, cudaEventRecord(h->ev_edges, s));
+        rc = pf_step_field_rows(h, h->strip_dep0, h->strip_dep1, stream);
+        if (rc) return rc;
+        predep_c = true;
+      } else if (handing && h->strip_one_launch_opt == 2 && h->tile_pending) {
         // the handed rows, the band below them and the last row (peer stores included) in one launch: the tiles of
         // the band simply have no passengers
         rc = launch_stencil(h, h->strip_dep0, rows, s, true, false, true);
@@ -1698,14 +1743,16 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
         rc = launch_stencil(h, mid, hi, s);
         if (rc) return rc;
       }
-      rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
-      if (rc) return rc;
-      if (rows > 1 && !last_done) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
+      if (!predep) {
+        rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
+        if (rc) return rc;
+        if (rows > 1 && !last_done) { rc = launch_stencil(h, rows - 1, rows, s); if (rc) return rc; }
+      }
     }
     rc = pf_swap(h);
     if (rc) return rc;
     STRIP_MARK();  // 6: stencil
-    const bool mig_side = move && !h->strip_mig_inline;
+    const bool mig_side = mig_side_c;
     cudaStream_t ms = mig_side ? h->side : s;
     if (move && (h->peer_up.set || h->peer_dn.set)) {
       k_peer_wait<<<1, 1, 0, ms>>>(h->peer_up.set ? h->peer_flags + 2 : nullptr, h->peer_dn.set ? h->peer_flags + 3 : nullptr,
@@ -1714,6 +1761,12 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     }
     STRIP_MARK();  // 7: migration wait
     if (move) { rc = strip_unpack(h, a, ms); if (rc) return rc; }
+    if (predep_c) {  // the EARLY part of the next tick's deposit: behind the unpack and this tick's edge rows
+      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_edges, 0));
+      rc = agents_deposit(h, a, h->side, 1, 0);
+      if (rc) return rc;
+      h->strip_predep = true;
+    }
     if (mig_side) {  // join: everything the caller enqueues next is ordered behind the unpack
       PF_CUDA(h, cudaEventRecord(h->ev_join, h->side));
       PF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));

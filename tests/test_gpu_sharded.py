@@ -52,7 +52,7 @@ def test_strips_equal_unsharded_bitexact(world, variant, peer):
         w.b.field.close()
 
 
-@pytest.mark.parametrize("peer", [False, True, "one-launch", "fold-below", "part-a-1"])
+@pytest.mark.parametrize("peer", [False, True, "one-launch", "fold-below", "part-a-1", "no-predeposit", "mig-inline"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
     # strips tall enough to have interior tile rows (64 rows x 1024 columns): the move kernel hands the
@@ -74,6 +74,10 @@ def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
             strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, 1)
         if peer == "fold-below":  # the handed rows, the band below them and the last row in one launch (value 2)
             strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, 2)
+        if peer == "no-predeposit":  # the whole deposit at the start of the tick (default: in two parts, see pf_strip_tick)
+            strip.field.set_option(abi.OPT_STRIP_NO_PREDEPOSIT, 1)
+        if peer == "mig-inline":     # migration in line with the stencil launches (and therefore no early deposit either)
+            strip.field.set_option(abi.OPT_STRIP_MIG_INLINE, 1)
         if peer == "part-a-1":    # only the first tile row runs before the move kernel; every other row hands over
             strip.field.set_option(abi.OPT_STRIP_PART_A_TILES, 1)
         workers.append(sharded.StripWorker(strip, r, world))
@@ -102,7 +106,8 @@ def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
         w.b.field.close()
 
 
-def test_strip_hand_over_falls_back_when_an_interior_tile_is_crowded():
+@pytest.mark.parametrize("peer", [False, True])
+def test_strip_hand_over_falls_back_when_an_interior_tile_is_crowded(peer):
     # 5000 robots inside one interior tile of strip 0: its bin overflows, the flag is raised on the device,
     # the stencil leaves its output alone and the NEXT tick's key kernel deposits the handed robots after
     # all (with the amount their already bumped counter says); the tile is marked dense and its later deposits go
@@ -124,6 +129,8 @@ def test_strip_hand_over_falls_back_when_an_interior_tile_is_crowded():
         strip.field.set_option(abi.OPT_FORCE_OWNER_DEPOSIT, 1)
         workers.append(sharded.StripWorker(strip, r, world))
     drv = sharded.LocalDriver(workers)
+    if peer:  # pf_strip_tick: the deposit in two parts — the LATE part (handed robots) has real work on the fall-back tick
+        drv.attach_peers()
     for w in workers:
         w.b.sort_agents()
     for t in range(nticks):
