@@ -474,6 +474,8 @@ int pf_heatmap_snapshot_host(pf_heatmap* h, double* dst_host, void* stream);
                                         tick the NEXT tick's deposit of the robots that were not handed over — edge bands and
                                         arrivals — runs at the end of the tick on the side stream, behind the unpack and beside
                                         the stencil launch that carries the handed robots' deposits) */
+#define PF_OPT_STRIP_EDGES_SIDE 13 /* pf_strip_tick: the small stencil launches of a hand-over tick (first rows, band below the
+                                     handed rows, the two edge rows) on the side stream as well (default 0: measured slower) */
 #define PF_OPT_PEER_TIMEOUT_MS 7 /* bound of the peer waits in milliseconds (default 5000) */
 #define PF_OPT_USE_GRAPH 3      /* pf_step: replay pairs of ticks from a CUDA graph (default: on for
                                    fields of <= 2^24 floats per buffer, where a tick is launch-bound) */

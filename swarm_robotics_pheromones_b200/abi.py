@@ -43,6 +43,7 @@ OPT_STRIP_ONE_LAUNCH = 8
 OPT_STRIP_PART_A_TILES = 9
 OPT_STRIP_MIG_INLINE = 11
 OPT_STRIP_NO_PREDEPOSIT = 12
+OPT_STRIP_EDGES_SIDE = 13
 TICK_A, TICK_B, TICK_C, TICK_ALL = 0x1, 0x2, 0x4, 0x7
 STEP_DEPOSIT, STEP_SENSE, STEP_FIELD, STEP_MOVE, STEP_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 STEP_HANDOVER = 0x10  # pf_agents_step on a strip: interior rows hand their next deposit to the stencil

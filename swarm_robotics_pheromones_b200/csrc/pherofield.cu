@@ -99,6 +99,9 @@ struct pf_handle {
   int strip_no_predeposit;    // PF_OPT_STRIP_NO_PREDEPOSIT
   bool strip_predep;          // the EARLY part of the next tick's deposit is enqueued (behind this tick's unpack)
   cudaEvent_t ev_edges;       // the strip's edge rows of this tick are stepped
+  cudaEvent_t ev_a, ev_halo;  // phase B has begun (deposit done) / the ghost rows are in
+  int strip_edges_side_opt;   // PF_OPT_STRIP_EDGES_SIDE
+  bool strip_edges_side;      // this tick's small stencil launches (first rows, band below, edge rows) went to the side stream
   // pf_strip_tick phase marks (profiling enabled): kStripSlots ticks x kStripMarks events, folded into strip_ms
   cudaEvent_t* strip_ev;
   int strip_used, strip_mark;
@@ -367,6 +370,8 @@ extern "C" int pf_create(const pf_config* cfg, pf_handle** out) {
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_edges, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
   {
     int occ = 0;
     CREATE_CUDA(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -416,6 +421,8 @@ extern "C" int pf_destroy(pf_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_edges) cudaEventDestroy(h->ev_edges);
+  if (h->ev_a) cudaEventDestroy(h->ev_a);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
   if (h->g_graph) cudaGraphDestroy(h->g_graph);
   if (h->prof_ev) {
@@ -717,6 +724,7 @@ extern "C" int pf_set_option(pf_handle* h, int option, int value) {
   if (option == PF_OPT_STRIP_PART_A_TILES) { h->strip_part_a_tiles = value > 0 ? value : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_ONE_LAUNCH) { h->strip_one_launch_opt = value < 0 ? 0 : (value > 2 ? 2 : value); return PF_OK; }
   if (option == PF_OPT_STRIP_MIG_INLINE) { h->strip_mig_inline = value ? 1 : 0; return PF_OK; }
+  if (option == PF_OPT_STRIP_EDGES_SIDE) { h->strip_edges_side_opt = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_STRIP_NO_PREDEPOSIT) { h->strip_no_predeposit = value ? 1 : 0; return PF_OK; }
   if (option == PF_OPT_PEER_TIMEOUT_MS) { h->peer_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull; return PF_OK; }
   if (option == PF_OPT_USE_GRAPH) { h->use_graph = value ? 1 : 0; if (!value) graph_drop(h); return PF_OK; }
@@ -1677,10 +1685,30 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
   const int mid = one_launch ? lo : (handing ? h->strip_dep0 : lo + (hi - lo) / 2);
   if (phases & PF_TICK_B) {  // interior rows while the halo is in flight, halo wait, agents, leavers out
     if (!h->strip_active) return set_err(h, PF_ESTATE, "pf_strip_tick: phase B without phase A");
-    if (mid > lo) { rc = launch_stencil(h, lo, mid, s); if (rc) return rc; }
+    // PF_OPT_STRIP_EDGES_SIDE (off by default): on a hand-over tick with the deposit in two parts the small stencil
+    // launches leave the caller's stream altogether — the first rows start on the side stream at once (they need
+    // neither the halo nor the agents), the band below the handed rows and the two edge rows follow there as soon as
+    // the ghost rows are in. Measured at 8 x 4096 rows: 0.679 ms per strip tick against 0.567 in line — the
+    // high-priority launches take SM slots from the move kernel's single resident wave and from each other.
+    const bool edges_side = handing && !one_launch && move && !h->strip_mig_inline && dep && a->n > 0 &&
+                            !h->strip_no_predeposit && h->strip_edges_side_opt && h->strip_one_launch_opt != 2 &&
+                            (h->peer_up.set || h->peer_dn.set);
+    h->strip_edges_side = edges_side;
+    if (edges_side) {
+      PF_CUDA(h, cudaEventRecord(h->ev_a, s));
+      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_a, 0));
+    }
+    if (mid > lo) { rc = launch_stencil(h, lo, mid, edges_side ? h->side : s); if (rc) return rc; }
     STRIP_MARK();  // 2: signal + stencil over the first rows
     rc = pf_peer_wait(h, stream);
     if (rc) return rc;
+    if (edges_side) {
+      PF_CUDA(h, cudaEventRecord(h->ev_halo, s));
+      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_halo, 0));
+      if (h->strip_dep1 < rows) { rc = launch_stencil(h, h->strip_dep1, rows, h->side); if (rc) return rc; }
+      rc = launch_stencil(h, 0, rows < 1 ? rows : 1, h->side);
+      if (rc) return rc;
+    }
     STRIP_MARK();  // 3: halo wait + ghost rows
     if (a->n > 0 && (flags & (PF_STEP_SENSE | PF_STEP_MOVE))) {
       const uint32_t f = (flags & (PF_STEP_SENSE | PF_STEP_MOVE)) | (handing ? PF_STEP_HANDOVER : 0u);
@@ -1718,11 +1746,15 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       // carries the handed robots' deposits; the next tick starts with its halo signal almost at once.
       const bool predep = handing && h->tile_pending && mig_side_c && dep && a->n > 0 && !h->strip_no_predeposit &&
                           h->strip_one_launch_opt != 2 && (h->peer_up.set || h->peer_dn.set);
+      if (h->strip_edges_side && !predep)
+        return set_err(h, PF_ESTATE, "pf_strip_tick: the tick's options changed between phases B and C");
       if (predep) {
-        if (h->strip_dep1 < rows) { rc = launch_stencil(h, h->strip_dep1, rows, s); if (rc) return rc; }
-        rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
-        if (rc) return rc;
-        PF_CUDA(h, cudaEventRecord(h->ev_edges, s));
+        if (!h->strip_edges_side) {  // (else they are on the side stream already, in front of the migration kernels)
+          if (h->strip_dep1 < rows) { rc = launch_stencil(h, h->strip_dep1, rows, s); if (rc) return rc; }
+          rc = launch_stencil(h, 0, rows < 1 ? rows : 1, s);
+          if (rc) return rc;
+          PF_CUDA(h, cudaEventRecord(h->ev_edges, s));
+        }
         rc = pf_step_field_rows(h, h->strip_dep0, h->strip_dep1, stream);
         if (rc) return rc;
         predep_c = true;
@@ -1762,7 +1794,7 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
     STRIP_MARK();  // 7: migration wait
     if (move) { rc = strip_unpack(h, a, ms); if (rc) return rc; }
     if (predep_c) {  // the EARLY part of the next tick's deposit: behind the unpack and this tick's edge rows
-      PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_edges, 0));
+      if (!h->strip_edges_side) PF_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_edges, 0));
       rc = agents_deposit(h, a, h->side, 1, 0);
       if (rc) return rc;
       h->strip_predep = true;
@@ -1779,6 +1811,7 @@ extern "C" int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, u
       h->strip_used++;
     }
     h->strip_active = false;
+    h->strip_edges_side = false;
     h->strip_one_launch = false;
     h->strip_dep0 = h->strip_dep1 = 0;
   }

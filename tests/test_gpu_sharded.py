@@ -52,7 +52,7 @@ def test_strips_equal_unsharded_bitexact(world, variant, peer):
         w.b.field.close()
 
 
-@pytest.mark.parametrize("peer", [False, True, "one-launch", "fold-below", "part-a-1", "no-predeposit", "mig-inline"])
+@pytest.mark.parametrize("peer", [False, True, "one-launch", "fold-below", "part-a-1", "no-predeposit", "mig-inline", "edges-side"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
     # strips tall enough to have interior tile rows (64 rows x 1024 columns): the move kernel hands the
@@ -76,6 +76,8 @@ def test_strips_hand_deposits_to_the_stencil_bitexact(world, peer):
             strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, 2)
         if peer == "no-predeposit":  # the whole deposit at the start of the tick (default: in two parts, see pf_strip_tick)
             strip.field.set_option(abi.OPT_STRIP_NO_PREDEPOSIT, 1)
+        if peer == "edges-side":     # two-part deposit with the small stencil launches on the side stream as well
+            strip.field.set_option(abi.OPT_STRIP_EDGES_SIDE, 1)
         if peer == "mig-inline":     # migration in line with the stencil launches (and therefore no early deposit either)
             strip.field.set_option(abi.OPT_STRIP_MIG_INLINE, 1)
         if peer == "part-a-1":    # only the first tile row runs before the move kernel; every other row hands over

@@ -26,6 +26,7 @@ ap.add_argument("--config", default="c3")
 ap.add_argument("--one-launch", type=int, default=-1, help="PF_OPT_STRIP_ONE_LAUNCH (0, 1, 2); -1 = the library default")
 ap.add_argument("--mig-inline", type=int, default=-1, help="PF_OPT_STRIP_MIG_INLINE; -1 = the library default")
 ap.add_argument("--no-predeposit", type=int, default=-1, help="PF_OPT_STRIP_NO_PREDEPOSIT; -1 = the library default")
+ap.add_argument("--edges-side", type=int, default=-1, help="PF_OPT_STRIP_EDGES_SIDE; -1 = the library default")
 ap.add_argument("--strips", type=int, default=0, help="materialise only the first K strips (0 = all): saves memory")
 args = ap.parse_args()
 
@@ -43,6 +44,8 @@ for r in range(G):
         strip.field.set_option(abi.OPT_STRIP_ONE_LAUNCH, args.one_launch)
     if args.no_predeposit >= 0:
         strip.field.set_option(abi.OPT_STRIP_NO_PREDEPOSIT, args.no_predeposit)
+    if args.edges_side >= 0:
+        strip.field.set_option(abi.OPT_STRIP_EDGES_SIDE, args.edges_side)
     if args.mig_inline >= 0:
         strip.field.set_option(abi.OPT_STRIP_MIG_INLINE, args.mig_inline)
     workers.append(sharded.StripWorker(strip, r, G))
