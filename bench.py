@@ -95,8 +95,9 @@ def stencil_traffic_from_profile():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    def __init__(self, index: int):
+    def __init__(self, index: int, first_delay_s: float = 0.004):
         self.index = index
+        self.first_delay_s = float(os.environ.get("PF_BENCH_SAMPLER_DELAY_S", first_delay_s))
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -119,7 +120,11 @@ class ClockSampler:
             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
         }
-        while not self._stop.is_set():
+        # NVML queries take the driver's global lock (every rank's sampler at the same instant, right behind the
+        # barrier, in front of the first timed tick): the first sample is taken a few milliseconds into the timed
+        # region instead of at its first instruction
+        self._stop.wait(self.first_delay_s)
+        while True:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -128,6 +133,8 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
+            if self._stop.is_set():
+                break
             self._stop.wait(0.05)
 
     def start(self):
@@ -455,9 +462,9 @@ def run_single(args):
     state = {"since_sort": args.sort_every, "sorts": 0}  # first call sorts the initial population
 
     # ---- device-resident throughput
+    sampler = ClockSampler(0)   # (NVML initialised before the warm-up: no idle gap between warm-up and timed region)
     run_ticks(args.warmup)
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
     l0 = field.launch_count()
     # launch-bound (small) problems replay ticks from a CUDA graph, which per-phase event profiling
     # would disable: time them unprofiled and take the phase split from a second, profiled pass
@@ -764,12 +771,12 @@ def run_sharded(args):
         drv.tick(True, hand_over=not (last or before_sort or args.no_hand_over))
         tick_no[0] += 1
 
+    sampler = ClockSampler(local)   # (NVML initialised before the warm-up: no idle gap in front of the timed region)
     for k in range(args.warmup):
         tick(last=k == args.warmup - 1)
     torch.cuda.synchronize()
     dist.barrier()
     tick_no[0] = 0  # the timed region pays ceil(K / sort_every) sorts
-    sampler = ClockSampler(local)
     if args.phase_profile and not legacy:
         strip.field.profile(True)   # CUDA events at the phase boundaries inside pf_strip_tick
     l0 = strip.field.launch_count()
