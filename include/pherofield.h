@@ -343,6 +343,14 @@ int pf_peer_status(pf_handle* h, void* stream);
  *   A: deposit -> halo signal
  *   B: stencil over the first rows -> halo wait -> sense/decide/move (+ hand-over) -> pack leavers -> migration signal
  *   C: stencil over the remaining rows (handed deposits ride along) -> swap -> migration wait -> unpack
+ * With PF_STEP_MOVE the migration kernels (pack, signal, wait, unpack) run on the handle's own side stream, beside
+ * the stencil launches of phase C, and `stream` joins them before the call's last kernel: for the caller the tick
+ * remains one ordered unit of work on `stream`. On a PF_STEP_HANDOVER tick the side stream goes one step further
+ * behind the unpack: the NEXT tick's deposit of the robots that were not handed over (edge bands, arrivals) — that
+ * tick's phase A then only deposits the handed robots, i.e. nothing unless the stencil could not apply them. A
+ * hand-over tick must therefore be followed by a tick with PF_STEP_DEPOSIT (PF_ESTATE otherwise), and poses replaced
+ * in between (pf_agents_observe) do not change where that tick's deposits went: all of them were taken at the poses
+ * this tick's move kernel produced. PF_OPT_STRIP_MIG_INLINE / PF_OPT_STRIP_NO_PREDEPOSIT keep everything in line.
  * Replaces Controller.startPheromone / homing (sup:565-607, 627-663) on a strip; order as pf_step. */
 #define PF_TICK_A 0x1u
 #define PF_TICK_B 0x2u
@@ -353,7 +361,9 @@ int pf_strip_tick(pf_handle* h, const pf_agents* a, uint32_t flags, uint32_t pha
 /* Per-phase device times of pf_strip_tick while profiling is enabled (pf_profile_enable), summed over `ticks`:
  * [0] deposit, [1] halo signal + stencil over the first rows, [2] halo wait + ghost rows, [3] sense/decide/move
  * (+ hand-over bins and grouping), [4] pack + migration signal, [5] stencil over the remaining rows, [6] migration
- * wait, [7] unpack, [8..10] unused. Synchronises the device. */
+ * wait, [7] unpack, [8..10] unused. The marks are events on the caller's stream: what runs on the side stream
+ * (migration, the early part of the next deposit) shows up as the wait for it at the end of [7], and [4] / [6] are
+ * then enqueue times only. Synchronises the device. */
 int pf_strip_profile(pf_handle* h, double* ms_out11, uint64_t* ticks, int reset);
 
 /* pf_snapshot_host, pf_field_sum_host and pf_counters_host return PF_ESTATE between a hand-over tick and the next
