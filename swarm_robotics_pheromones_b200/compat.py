@@ -206,9 +206,11 @@ class ReferenceCompat:
 
     def tick_host_async(self, pose_host: torch.Tensor):
         """The tick as a pipeline over robot sub-ranges (the copies dominate: 12 B in, 9 B out per robot):
-          copy-in stream   H2D of chunk i            | main: observe chunk i as soon as it has landed
-          main stream      deposit (all robots), then decide chunk i -> evaporate+diffuse
-          copy-out stream  D2H of chunk i's speeds and decisions beside decide chunk i+1 and the field kernel
+          copy-in stream   x and y of every chunk first, the headings behind them
+          main stream      observe chunk i as soon as its x / y have landed; deposit (all robots: it needs no
+                           heading) beside the headings' H2D; then decide chunk i -> evaporate+diffuse
+          copy-out stream  D2H of chunk i's speeds and decisions beside decide chunk i+1, the rest of the headings'
+                           H2D (PCIe is full duplex) and the field kernel
         Before the start delay observe is skipped: the reference only stores poses inside deposit_pheromone
         (sup:279-289, 577), so the first deposit after t = 5 s is unconditional (old_pos is None, sup:261-262)."""
         f, sw = self.field, self.swarm
@@ -217,6 +219,7 @@ class ReferenceCompat:
             self._side = torch.cuda.Stream(f.device)       # copy-out
             self._cin = torch.cuda.Stream(f.device)        # copy-in
             self._ev_in = [torch.cuda.Event() for _ in range(self.CHUNKS)]
+            self._ev_th = [torch.cuda.Event() for _ in range(self.CHUNKS)]
             self._ev_dec = [torch.cuda.Event() for _ in range(self.CHUNKS)]
             self._ev_out = torch.cuda.Event()
             self._ev_free = torch.cuda.Event()
@@ -224,24 +227,27 @@ class ReferenceCompat:
         t, _ = f.time()
         sensing = t >= f.start_delay
         chunks = self._chunk_views()
-        self._cin.wait_event(self._ev_free)                # the previous tick's observe has consumed _d_pose
+        self._cin.wait_event(self._ev_free)                # the previous tick has consumed _d_pose
         with torch.cuda.stream(self._cin):
             for i, (a, b, _) in enumerate(chunks):
-                for r in range(3):  # row by row: contiguous 1-D copies (a strided 2-D one is staged by torch)
+                for r in range(2):  # row by row: contiguous 1-D copies (a strided 2-D one is staged by torch)
                     self._d_pose[r, a:b].copy_(pose_host[r, a:b], non_blocking=True)
                 self._ev_in[i].record(self._cin)
+            for i, (a, b, _) in enumerate(chunks):
+                self._d_pose[2, a:b].copy_(pose_host[2, a:b], non_blocking=True)
+                self._ev_th[i].record(self._cin)
         for i, (a, b, view) in enumerate(chunks):
             main.wait_event(self._ev_in[i])
-            if sensing:
-                f.observe(view, self._d_pose[0, a:], self._d_pose[1, a:], self._d_pose[2, a:])
+            if sensing:                                    # storingPosition + has_moved; the heading follows below
+                f.observe(view, self._d_pose[0, a:], self._d_pose[1, a:], None)
             else:                                          # poses only; no has_moved bookkeeping yet
                 sw.x[a:b].copy_(self._d_pose[0, a:b]); sw.y[a:b].copy_(self._d_pose[1, a:b])
-                sw.theta[a:b].copy_(self._d_pose[2, a:b])
-        self._ev_free.record(main)
         if sensing:
             f.agents_deposit(sw)
         self._side.wait_event(self._ev_out)                # (re-use of the staging: previous D2H done)
         for i, (a, b, view) in enumerate(chunks):
+            main.wait_event(self._ev_th[i])
+            sw.theta[a:b].copy_(self._d_pose[2, a:b])
             # decide on the main stream (two HBM-bound kernels side by side only slow each other down);
             # the kernel writes the u8 decisions itself
             f.agents_step(view, abi.STEP_SENSE if sensing else 0, decisions=self._d_dec[a:])
@@ -251,6 +257,7 @@ class ReferenceCompat:
                 self._h_out[0, a:b].copy_(sw.wl[a:b], non_blocking=True)
                 self._h_out[1, a:b].copy_(sw.wr[a:b], non_blocking=True)
                 self._h_dec[a:b].copy_(self._d_dec[a:b], non_blocking=True)
+        self._ev_free.record(main)
         self._ev_out.record(self._side)
         f.step(sw, 1, abi.STEP_FIELD)  # evaporate+diffuse only; advances the tick clock
         main.wait_event(self._ev_out)

@@ -138,6 +138,57 @@ def test_tick_host_equals_oracle_without_move():
     rc.close()
 
 
+def test_tick_host_pipeline_over_robot_chunks_equals_oracle():
+    # 70 000 robots: tick_host runs as a pipeline over four robot sub-ranges (x / y of every chunk first, observe per
+    # chunk, one deposit beside the headings' H2D, decide + D2H per chunk); heading-relative sensing on a random
+    # two-channel field, so a heading that arrived late or in the wrong chunk would change decisions
+    cfg = abi.default_config(512, 512, 2)
+    cfg.stencil = 9
+    for c in range(2):
+        cfg.diffusion[c] = 0.1
+    rng = np.random.default_rng(3)
+    n = 70000
+    assert n >= (1 << 16)
+    x = rng.uniform(0.1, 5.0, n).astype(np.float32)
+    y = rng.uniform(0.1, 5.0, n).astype(np.float32)
+    th = rng.uniform(-3, 3, n).astype(np.float32)
+    f0 = rng.random((2, 512, 512), dtype=np.float32)
+    rc = ReferenceCompat(cfg, [str(i) for i in range(n)], np.stack([x, y], 1), headings=th, start_delay=0.0)
+    assert len(rc._chunk_views()) == 4
+    rc.field.upload(f0)
+    o = dense.DenseOracle(cfg)
+    o.set_field(f0)
+    a = dense.AgentsNP(x, y, th)
+    pose = torch.empty((3, n)).pin_memory()
+    seen = np.zeros(6, np.int64)
+    for t in range(6):
+        x = (x + rng.uniform(-0.004, 0.004, n)).astype(np.float32)
+        y = (y + rng.uniform(-0.004, 0.004, n)).astype(np.float32)
+        th = (th + rng.uniform(-0.3, 0.3, n)).astype(np.float32)
+        pose[0].copy_(torch.from_numpy(x)); pose[1].copy_(torch.from_numpy(y)); pose[2].copy_(torch.from_numpy(th))
+        wl, wr, dec = rc.tick_host(pose)
+        if t == 0:
+            moved = np.ones(n, bool)
+        else:
+            dx, dy = x - a.x, y - a.y
+            moved = np.sqrt(dx * dx + dy * dy, dtype=np.float32) >= np.float32(0.0015)
+        a.x[:], a.y[:], a.theta[:] = x, y, th
+        a.meta = (a.meta & ~np.uint32(abi.META_MOVED)) | np.where(moved, abi.META_MOVED, 0).astype(np.uint32) | np.uint32(abi.META_HASPOS)
+        o.agents_deposit(a)
+        d = o.agents_step(a, abi.STEP_SENSE)
+        o.step_field(1)
+        assert (dec.numpy() == d).all(), f"tick {t}: {(dec.numpy() != d).sum()} decisions differ"
+        assert (wl.numpy().view(np.uint32) == a.wl.view(np.uint32)).all()
+        assert (wr.numpy().view(np.uint32) == a.wr.view(np.uint32)).all()
+        seen += np.bincount(d, minlength=6)
+    assert seen[abi.DEC_LEFT] > 0 and seen[abi.DEC_RIGHT] > 0 and seen[abi.DEC_STRAIGHT] > 0
+    got = rc.swarm.to_numpy()
+    assert (got["theta"].view(np.uint32) == a.theta.view(np.uint32)).all()
+    torch.cuda.synchronize()
+    assert (rc.field.snapshot().view(np.uint32) == np.ascontiguousarray(o.field).view(np.uint32)).all()
+    rc.close()
+
+
 def test_first_deposit_after_the_start_delay_is_unconditional_for_a_stationary_robot():
     # the reference stores poses only inside deposit_pheromone (sup:279-289, called from t >= 5 s on), so
     # the first deposit has no previous pose and is unconditional (old_pos is None -> True, sup:261-262) — even for a
